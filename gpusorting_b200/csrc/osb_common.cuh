@@ -1,0 +1,62 @@
+// osb_common.cuh -- constants, tile-descriptor format and PTX helpers shared by the sm_100a kernels.
+//
+// Domain vocabulary follows the reference (b0nes164/GPUSorting, GPUSortingCUDA/Sort/OneSweep.cu):
+// digit place, partition tile, tile reduction / inclusive prefix, chained scan with decoupled lookback.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace osb {
+
+constexpr int kRadix = 256;      // bins per digit place          (reference: RADIX, OneSweep.cu:17)
+constexpr int kRadixLog = 8;     // bits per digit                (reference: RADIX_LOG, OneSweep.cu:19)
+
+// ---- chained-scan tile descriptor -------------------------------------------------------------------
+// One 64-bit word per (tile, digit):  [63:40] epoch | [39:2] value | [1:0] flag.
+// The reference packs {value:30, flag:2} into 32 bits (OneSweep.cu:39-42), which caps n at 2^30 and
+// forces a memset of every descriptor before every sort (OneSweepDispatcher.cuh:301-309).  Here the value
+// field is 38 bits (n <= 2^38 per GPU) and the epoch field makes stale words from earlier passes / sorts
+// read as NOT_READY, so descriptors are never cleared between sorts.
+constexpr uint64_t kFlagNotReady = 0;   // reference: FLAG_NOT_READY
+constexpr uint64_t kFlagReduction = 1;  // reference: FLAG_REDUCTION (tile-local digit count published)
+constexpr uint64_t kFlagInclusive = 2;  // reference: FLAG_INCLUSIVE (prefix over tiles 0..p published)
+constexpr uint64_t kFlagMask = 3;
+constexpr int kValueBits = 38;
+constexpr int kEpochShift = 40;
+constexpr uint32_t kEpochMax = (1u << 24) - 1;
+
+__host__ __device__ __forceinline__ uint64_t desc_pack(uint32_t epoch, uint64_t flag, uint64_t value)
+{
+    return (static_cast<uint64_t>(epoch) << kEpochShift) | (value << 2) | flag;
+}
+__host__ __device__ __forceinline__ uint64_t desc_value(uint64_t d) { return (d >> 2) & ((1ull << kValueBits) - 1); }
+__host__ __device__ __forceinline__ uint32_t desc_epoch(uint64_t d) { return static_cast<uint32_t>(d >> kEpochShift); }
+
+// ---- PTX helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lane_id() { uint32_t v; asm("mov.u32 %0, %%laneid;" : "=r"(v)); return v; }
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t v; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(v)); return v; }
+
+// Descriptors carry flag and value in one naturally-atomic 64-bit word, so relaxed GPU-scope accesses are
+// sufficient (no separate payload to order against); .gpu scope keeps them out of the non-coherent L1.
+__device__ __forceinline__ uint64_t ld_relaxed_gpu_u64(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u64(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Streaming loads/stores: every key is read once and written once per pass; do not let them displace the
+// descriptor words (which are re-read by successor tiles) from L1/L2 earlier than necessary.
+template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
+
+template <typename KeyT> __device__ __forceinline__ uint32_t digit_of(KeyT k, uint32_t shift)
+{
+    return static_cast<uint32_t>(k >> shift) & (kRadix - 1);
+}
+
+}  // namespace osb

@@ -1,0 +1,390 @@
+// osb_host.cu -- host driver + C-ABI (include/onesweep_b200.h) of the B200 OneSweep sort.
+//
+// The sorter object plays the role of the reference's OneSweepDispatcher (Sort/OneSweepDispatcher.cuh:17-83):
+// it owns the ping-pong buffers and the control state and issues the launch plan of
+// OneSweepDispatcher.cuh:311-363 -- GlobalHistogram, Scan, then one DigitBinningPass per digit place,
+// ping-ponging keys -> alt -> keys.  Differences, all deliberate:
+//   * no per-sort memset of the tile descriptors (epoch-stamped 64-bit descriptors); one 8.3 KB memset of the
+//     control block (global histogram + tile tickets) per sort instead of 6 memsets over ~573 MB at n=2^30;
+//   * no host synchronisation inside the sort; everything is enqueued on the caller's stream;
+//   * the caller owns keys/values.
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/onesweep_b200.h"
+#include "osb_kernels.cuh"
+#include "osb_common.cuh"
+
+namespace {
+
+constexpr int kVersion = 1001;
+constexpr int kMaxPlaces = 8;
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? OSB200_OK : OSB200_ERR_CUDA - static_cast<int>(e); }
+
+#define OSB_TRY(expr)                                      \
+    do {                                                   \
+        cudaError_t e__ = (expr);                          \
+        if (e__ != cudaSuccess) return cuda_status(e__);   \
+    } while (0)
+
+// Control block, zeroed by ONE memset per sort: [ghist: 8*256 u64][tickets: 8 u32 (padded)]
+struct ControlLayout {
+    static constexpr size_t ghist_bytes = kMaxPlaces * osb::kRadix * sizeof(unsigned long long);
+    static constexpr size_t ticket_bytes = 64;  // 8 u32 tickets, padded
+    static constexpr size_t zeroed_bytes = ghist_bytes + ticket_bytes;
+    static constexpr size_t gbase_bytes = kMaxPlaces * osb::kRadix * sizeof(unsigned long long);
+    static constexpr size_t err_bytes = 64;
+    static constexpr size_t total = zeroed_bytes + gbase_bytes + err_bytes;
+};
+
+}  // namespace
+
+struct osb200_sorter {
+    int device = 0;
+    int sm_count = 148;
+    uint64_t max_n = 0;
+    int key_bytes = 4;
+    int value_bytes = 0;
+    osb::BinningConfig cfg;
+    bool atomic_order_ok = false;
+
+    void* alt_keys = nullptr;
+    uint32_t* alt_vals = nullptr;
+    unsigned char* control = nullptr;  // ControlLayout
+    uint64_t* desc = nullptr;          // [tiles][256]
+    uint64_t desc_tiles = 0;
+    uint32_t epoch = 0;
+
+    // lazily created staging for the host-buffer entry points
+    void* stage_keys = nullptr;
+    uint32_t* stage_vals = nullptr;
+    cudaStream_t own_stream = nullptr;
+
+    unsigned long long* ghist() const { return reinterpret_cast<unsigned long long*>(control); }
+    uint32_t* tickets() const { return reinterpret_cast<uint32_t*>(control + ControlLayout::ghist_bytes); }
+    unsigned long long* gbase() const { return reinterpret_cast<unsigned long long*>(control + ControlLayout::zeroed_bytes); }
+    unsigned long long* err() const
+    {
+        return reinterpret_cast<unsigned long long*>(control + ControlLayout::zeroed_bytes + ControlLayout::gbase_bytes);
+    }
+};
+
+namespace {
+
+uint64_t tiles_for(uint64_t n, uint32_t tile_keys) { return (n + tile_keys - 1) / tile_keys; }
+
+uint32_t smallest_tile(int key_bytes, bool pairs)
+{
+    // descriptors are sized for the smallest tile any variant may use
+    osb::BinningConfig c;
+    uint32_t t = osb::binning_tile_keys(key_bytes, pairs, c);
+    c.variant = osb::kVariantPersistent;
+    const uint32_t t2 = osb::binning_tile_keys(key_bytes, pairs, c);
+    return t2 < t ? t2 : t;
+}
+
+// advance the epoch; on wrap-around clear the descriptors once (every ~16M passes)
+int next_epoch(osb200_sorter* s, cudaStream_t stream, uint32_t* out)
+{
+    if (s->epoch >= osb::kEpochMax) {
+        OSB_TRY(cudaMemsetAsync(s->desc, 0, s->desc_tiles * osb::kRadix * sizeof(uint64_t), stream));
+        s->epoch = 0;
+    }
+    *out = ++s->epoch;
+    return OSB200_OK;
+}
+
+int check_handle(const osb200_sorter* s) { return s ? OSB200_OK : OSB200_ERR_INVALID_ARG; }
+
+// The launch plan (reference: OneSweepDispatcher.cuh:311-363).
+int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cudaStream_t stream)
+{
+    if (n <= 1) return OSB200_OK;
+    if (n > s->max_n) return OSB200_ERR_SIZE;
+    if (!d_keys || (reinterpret_cast<uintptr_t>(d_keys) & 15u)) return OSB200_ERR_INVALID_ARG;
+    if (s->value_bytes && !d_vals) return OSB200_ERR_INVALID_ARG;
+    const int places = s->key_bytes;
+
+    OSB_TRY(cudaMemsetAsync(s->control, 0, ControlLayout::zeroed_bytes, stream));
+    OSB_TRY(osb::launch_global_histogram(d_keys, n, s->key_bytes, s->ghist(), s->sm_count, stream));
+    OSB_TRY(osb::launch_scan(s->ghist(), s->gbase(), places, stream));
+
+    void* src = d_keys;
+    void* dst = s->alt_keys;
+    uint32_t* sv = d_vals;
+    uint32_t* dv = d_vals ? s->alt_vals : nullptr;
+    for (int p = 0; p < places; ++p) {
+        uint32_t epoch = 0;
+        int st = next_epoch(s, stream, &epoch);
+        if (st != OSB200_OK) return st;
+        OSB_TRY(osb::launch_digit_binning(src, dst, sv, dv, n, s->key_bytes, static_cast<uint32_t>(p) * 8u,
+                                          s->gbase() + p * osb::kRadix, s->desc, s->tickets() + p, epoch, s->cfg, stream));
+        void* t = src; src = dst; dst = t;
+        uint32_t* tv = sv; sv = dv; dv = tv;
+    }
+    return OSB200_OK;  // even number of passes: result is back in d_keys / d_vals
+}
+
+int ensure_staging(osb200_sorter* s)
+{
+    if (!s->own_stream) OSB_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    if (!s->stage_keys) {
+        if (cudaMalloc(&s->stage_keys, s->max_n * s->key_bytes) != cudaSuccess) return OSB200_ERR_ALLOC;
+    }
+    if (s->value_bytes && !s->stage_vals) {
+        if (cudaMalloc(&s->stage_vals, s->max_n * sizeof(uint32_t)) != cudaSuccess) return OSB200_ERR_ALLOC;
+    }
+    return OSB200_OK;
+}
+
+int sort_host_impl(osb200_sorter* s, void* h_keys, uint32_t* h_vals, uint64_t n)
+{
+    if (n <= 1) return OSB200_OK;
+    if (n > s->max_n) return OSB200_ERR_SIZE;
+    if (!h_keys || (s->value_bytes && !h_vals)) return OSB200_ERR_INVALID_ARG;
+    int st = ensure_staging(s);
+    if (st != OSB200_OK) return st;
+    cudaStream_t q = s->own_stream;
+    OSB_TRY(cudaMemcpyAsync(s->stage_keys, h_keys, n * s->key_bytes, cudaMemcpyHostToDevice, q));
+    if (s->value_bytes) OSB_TRY(cudaMemcpyAsync(s->stage_vals, h_vals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, q));
+    st = sort_impl(s, s->stage_keys, s->value_bytes ? s->stage_vals : nullptr, n, q);
+    if (st != OSB200_OK) return st;
+    OSB_TRY(cudaMemcpyAsync(h_keys, s->stage_keys, n * s->key_bytes, cudaMemcpyDeviceToHost, q));
+    if (s->value_bytes) OSB_TRY(cudaMemcpyAsync(h_vals, s->stage_vals, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, q));
+    OSB_TRY(cudaStreamSynchronize(q));
+    return OSB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int osb200_version(void) { return kVersion; }
+
+const char* osb200_status_string(int status)
+{
+    switch (status) {
+        case OSB200_OK: return "ok";
+        case OSB200_ERR_INVALID_ARG: return "invalid argument";
+        case OSB200_ERR_SIZE: return "n exceeds the sorter's max_n";
+        case OSB200_ERR_UNSUPPORTED: return "unsupported key/value combination";
+        case OSB200_ERR_NO_DEVICE: return "no usable sm_100 CUDA device";
+        case OSB200_ERR_ALLOC: return "device allocation failed";
+        case OSB200_ERR_NCCL: return "NCCL error";
+        default: break;
+    }
+    if (status <= OSB200_ERR_CUDA) return cudaGetErrorString(static_cast<cudaError_t>(OSB200_ERR_CUDA - status));
+    return "unknown status";
+}
+
+uint64_t osb200_workspace_bytes(uint64_t max_n, int key_bytes, int value_bytes)
+{
+    if ((key_bytes != 4 && key_bytes != 8) || (value_bytes != 0 && value_bytes != 4)) return 0;
+    const uint64_t tiles = tiles_for(max_n ? max_n : 1, smallest_tile(key_bytes, value_bytes != 0));
+    return max_n * key_bytes + max_n * value_bytes + tiles * osb::kRadix * sizeof(uint64_t) + ControlLayout::total;
+}
+
+int osb200_create(osb200_handle* out, uint64_t max_n, int key_bytes, int value_bytes)
+{
+    if (!out) return OSB200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if ((key_bytes != 4 && key_bytes != 8) || (value_bytes != 0 && value_bytes != 4)) return OSB200_ERR_INVALID_ARG;
+    if (key_bytes == 8 && value_bytes != 0) return OSB200_ERR_UNSUPPORTED;
+    if (max_n == 0 || max_n > (1ull << 34)) return OSB200_ERR_INVALID_ARG;
+
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return OSB200_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) { cudaGetLastError(); return OSB200_ERR_NO_DEVICE; }
+    if (prop.major != 10) return OSB200_ERR_NO_DEVICE;  // sm_100a binary only: no fallback of any kind
+
+    osb200_sorter* s = new (std::nothrow) osb200_sorter();
+    if (!s) return OSB200_ERR_ALLOC;
+    s->device = dev;
+    s->sm_count = prop.multiProcessorCount;
+    s->cfg.sm_count = s->sm_count;
+    s->max_n = max_n;
+    s->key_bytes = key_bytes;
+    s->value_bytes = value_bytes;
+
+    cudaError_t e = osb::configure_kernels();
+    if (e != cudaSuccess) { delete s; return cuda_status(e); }
+
+    s->desc_tiles = tiles_for(max_n, smallest_tile(key_bytes, value_bytes != 0));
+    bool ok = cudaMalloc(&s->alt_keys, max_n * key_bytes) == cudaSuccess;
+    if (ok && value_bytes) ok = cudaMalloc(&s->alt_vals, max_n * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->control, ControlLayout::total) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->desc, s->desc_tiles * osb::kRadix * sizeof(uint64_t)) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); osb200_destroy(s); return OSB200_ERR_ALLOC; }
+    e = cudaMemset(s->desc, 0, s->desc_tiles * osb::kRadix * sizeof(uint64_t));  // epoch 0 == never valid
+    if (e == cudaSuccess) e = cudaMemset(s->control, 0, ControlLayout::total);
+
+    // Verify on THIS device the hardware property the atomic ranking depends on; otherwise use ballots.
+    if (e == cudaSuccess) e = osb::launch_atomic_order_selftest(s->err(), s->sm_count, nullptr);
+    unsigned long long mism = 1;
+    if (e == cudaSuccess) e = cudaMemcpy(&mism, s->err(), sizeof(mism), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { osb200_destroy(s); return cuda_status(e); }
+    s->atomic_order_ok = (mism == 0);
+    s->cfg.rank_mode = s->atomic_order_ok ? osb::kRankAtomic : osb::kRankBallot;
+    *out = s;
+    return OSB200_OK;
+}
+
+int osb200_destroy(osb200_handle h)
+{
+    if (!h) return OSB200_ERR_INVALID_ARG;
+    cudaFree(h->alt_keys);
+    cudaFree(h->alt_vals);
+    cudaFree(h->control);
+    cudaFree(h->desc);
+    cudaFree(h->stage_keys);
+    cudaFree(h->stage_vals);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return OSB200_OK;
+}
+
+int osb200_sort_keys_u32(osb200_handle h, uint32_t* d_keys, uint64_t n, void* stream)
+{
+    if (check_handle(h) != OSB200_OK || h->key_bytes != 4) return OSB200_ERR_INVALID_ARG;
+    // a pairs-capable sorter may sort keys only
+    const int vb = h->value_bytes;
+    h->value_bytes = 0;
+    const int st = sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream));
+    h->value_bytes = vb;
+    return st;
+}
+
+int osb200_sort_pairs_u32(osb200_handle h, uint32_t* d_keys, uint32_t* d_values, uint64_t n, void* stream)
+{
+    if (check_handle(h) != OSB200_OK || h->key_bytes != 4 || h->value_bytes != 4) return OSB200_ERR_INVALID_ARG;
+    if (n > 1 && !d_values) return OSB200_ERR_INVALID_ARG;
+    return sort_impl(h, d_keys, d_values, n, static_cast<cudaStream_t>(stream));
+}
+
+int osb200_sort_keys_u64(osb200_handle h, uint64_t* d_keys, uint64_t n, void* stream)
+{
+    if (check_handle(h) != OSB200_OK || h->key_bytes != 8) return OSB200_ERR_INVALID_ARG;
+    return sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream));
+}
+
+int osb200_sort_host_keys_u32(osb200_handle h, uint32_t* h_keys, uint64_t n)
+{
+    if (check_handle(h) != OSB200_OK || h->key_bytes != 4) return OSB200_ERR_INVALID_ARG;
+    const int vb = h->value_bytes;
+    h->value_bytes = 0;
+    const int st = sort_host_impl(h, h_keys, nullptr, n);
+    h->value_bytes = vb;
+    return st;
+}
+
+int osb200_sort_host_pairs_u32(osb200_handle h, uint32_t* h_keys, uint32_t* h_values, uint64_t n)
+{
+    if (check_handle(h) != OSB200_OK || h->key_bytes != 4 || h->value_bytes != 4) return OSB200_ERR_INVALID_ARG;
+    return sort_host_impl(h, h_keys, h_values, n);
+}
+
+int osb200_sort_host_keys_u64(osb200_handle h, uint64_t* h_keys, uint64_t n)
+{
+    if (check_handle(h) != OSB200_OK || h->key_bytes != 8) return OSB200_ERR_INVALID_ARG;
+    return sort_host_impl(h, h_keys, nullptr, n);
+}
+
+int osb200_global_histogram(osb200_handle h, const void* d_keys, uint64_t n, uint64_t* d_hist, void* stream)
+{
+    if (check_handle(h) != OSB200_OK || !d_hist || (n && !d_keys)) return OSB200_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(d_keys) & 15u) return OSB200_ERR_INVALID_ARG;
+    cudaStream_t q = static_cast<cudaStream_t>(stream);
+    OSB_TRY(cudaMemsetAsync(d_hist, 0, static_cast<size_t>(h->key_bytes) * osb::kRadix * sizeof(uint64_t), q));
+    if (n == 0) return OSB200_OK;
+    OSB_TRY(osb::launch_global_histogram(d_keys, n, h->key_bytes, reinterpret_cast<unsigned long long*>(d_hist),
+                                         h->sm_count, q));
+    return OSB200_OK;
+}
+
+int osb200_digit_binning_pass(osb200_handle h, const void* d_in, void* d_out, const uint32_t* d_in_values,
+                              uint32_t* d_out_values, uint64_t n, uint32_t radix_shift, void* stream)
+{
+    if (check_handle(h) != OSB200_OK) return OSB200_ERR_INVALID_ARG;
+    if (n == 0) return OSB200_OK;
+    if (!d_in || !d_out || d_in == d_out) return OSB200_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u)) return OSB200_ERR_INVALID_ARG;
+    if (n > h->max_n) return OSB200_ERR_SIZE;
+    if ((radix_shift & 7u) || radix_shift >= static_cast<uint32_t>(h->key_bytes) * 8u) return OSB200_ERR_INVALID_ARG;
+    if ((d_in_values != nullptr) != (d_out_values != nullptr)) return OSB200_ERR_INVALID_ARG;
+    if (d_in_values && (h->key_bytes != 4 || h->value_bytes != 4)) return OSB200_ERR_UNSUPPORTED;
+    cudaStream_t q = static_cast<cudaStream_t>(stream);
+    const int place = static_cast<int>(radix_shift / 8u);
+    OSB_TRY(cudaMemsetAsync(h->control, 0, ControlLayout::zeroed_bytes, q));
+    // GlobalHistogram + Scan give every place; only `place` is consumed here
+    OSB_TRY(osb::launch_global_histogram(d_in, n, h->key_bytes, h->ghist(), h->sm_count, q));
+    OSB_TRY(osb::launch_scan(h->ghist(), h->gbase(), h->key_bytes, q));
+    uint32_t epoch = 0;
+    int st = next_epoch(h, q, &epoch);
+    if (st != OSB200_OK) return st;
+    OSB_TRY(osb::launch_digit_binning(d_in, d_out, d_in_values, d_out_values, n, h->key_bytes, radix_shift,
+                                      h->gbase() + place * osb::kRadix, h->desc, h->tickets() + place, epoch, h->cfg, q));
+    return OSB200_OK;
+}
+
+int osb200_validate(osb200_handle h, const void* d_keys, uint64_t n, uint64_t* h_err_count, void* stream)
+{
+    if (check_handle(h) != OSB200_OK || !h_err_count) return OSB200_ERR_INVALID_ARG;
+    *h_err_count = 0;
+    if (n < 2) return OSB200_OK;
+    if (!d_keys) return OSB200_ERR_INVALID_ARG;
+    cudaStream_t q = static_cast<cudaStream_t>(stream);
+    OSB_TRY(cudaMemsetAsync(h->err(), 0, sizeof(unsigned long long), q));
+    OSB_TRY(osb::launch_validate(d_keys, n, h->key_bytes, h->err(), h->sm_count, q));
+    unsigned long long v = 0;
+    OSB_TRY(cudaMemcpyAsync(&v, h->err(), sizeof(v), cudaMemcpyDeviceToHost, q));
+    OSB_TRY(cudaStreamSynchronize(q));
+    *h_err_count = v;
+    return OSB200_OK;
+}
+
+int osb200_init_random_u32(uint32_t* d_keys, uint32_t* d_payload, uint64_t n, uint32_t and_count, uint32_t seed,
+                           int payload_is_index, void* stream)
+{
+    if (n == 0) return OSB200_OK;
+    if (!d_keys) return OSB200_ERR_INVALID_ARG;
+    OSB_TRY(osb::launch_init_random(d_keys, d_payload, n, and_count, seed, payload_is_index != 0,
+                                    static_cast<cudaStream_t>(stream)));
+    return OSB200_OK;
+}
+
+int osb200_set_option(osb200_handle h, const char* key, int64_t value)
+{
+    if (check_handle(h) != OSB200_OK || !key) return OSB200_ERR_INVALID_ARG;
+    if (!std::strcmp(key, "rank_mode")) {
+        if (value != osb::kRankAtomic && value != osb::kRankBallot) return OSB200_ERR_INVALID_ARG;
+        if (value == osb::kRankAtomic && !h->atomic_order_ok) return OSB200_ERR_UNSUPPORTED;
+        h->cfg.rank_mode = static_cast<int>(value);
+        return OSB200_OK;
+    }
+    if (!std::strcmp(key, "variant")) {
+        if (value != osb::kVariantTilePerCta && value != osb::kVariantPersistent) return OSB200_ERR_INVALID_ARG;
+        h->cfg.variant = static_cast<int>(value);
+        return OSB200_OK;
+    }
+    return OSB200_ERR_INVALID_ARG;
+}
+
+int64_t osb200_get_info(osb200_handle h, const char* key)
+{
+    if (check_handle(h) != OSB200_OK || !key) return OSB200_ERR_INVALID_ARG;
+    if (!std::strcmp(key, "tile_keys")) return osb::binning_tile_keys(h->key_bytes, h->value_bytes != 0, h->cfg);
+    if (!std::strcmp(key, "launches_per_sort")) return 2 + h->key_bytes;  // histogram + scan + one pass per place
+    if (!std::strcmp(key, "memsets_per_sort")) return 1;
+    if (!std::strcmp(key, "sm_count")) return h->sm_count;
+    if (!std::strcmp(key, "rank_mode")) return h->cfg.rank_mode;
+    if (!std::strcmp(key, "variant")) return h->cfg.variant;
+    if (!std::strcmp(key, "atomic_order_ok")) return h->atomic_order_ok ? 1 : 0;
+    if (!std::strcmp(key, "max_n")) return static_cast<int64_t>(h->max_n);
+    if (!std::strcmp(key, "epoch")) return h->epoch;
+    return OSB200_ERR_INVALID_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,519 @@
+// osb_kernels.cu -- hand-written sm_100a kernels of the OneSweep path.
+//
+// Three kernels per sort, as in the reference (GPUSortingCUDA/Sort/OneSweep.cu), each re-designed for B200:
+//   global_histogram_kernel  <-> OneSweep::GlobalHistogram        (OneSweep.cu:44-123)
+//   scan_kernel              <-> OneSweep::Scan                   (OneSweep.cu:125-162)
+//   digit_binning_kernel     <-> OneSweep::DigitBinningPassKeysOnly / Pairs (OneSweep.cu:164-344, 346-600)
+//
+// The B200 design point: at ~23 B/clk/SM of HBM bandwidth a binning pass must retire
+// ~2.3 keys per SM clock, which the reference's 8-ballots-per-key warp multisplit cannot issue (measured
+// 2.1 keys/clk/SM for the ballots alone, profiles/r01_microbench.md).  Ranking is therefore done with ONE
+// shared-memory atomicAdd per key on a warp-private histogram: on sm_100 the returning ATOMS.ADD hands its
+// values to same-address lanes of a warp instruction in ascending lane order (verified over 5e10 atomics and
+// re-verified by a device self-test when a sorter is created), i.e. it is a single-instruction stable
+// multisplit.  The ballot formulation is kept as RankMode::kRankBallot.
+#include "osb_kernels.cuh"
+#include "osb_common.cuh"
+
+namespace osb {
+
+// =====================================================================================================
+// GlobalHistogram
+// =====================================================================================================
+constexpr int kHistThreads = 512;
+constexpr int kHistCtasPerSm = 4;
+
+template <typename KeyT>
+__device__ __forceinline__ void hist_count_word(uint32_t* s_hist, uint32_t w, int word_in_vec)
+{
+    constexpr int PLACES = sizeof(KeyT);
+    // byte q of 32-bit word `word_in_vec` of a 16-byte vector is digit place ((word*4+q) % PLACES) of some key
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int place = (word_in_vec * 4 + q) % PLACES;
+        atomicAdd(&s_hist[place * kRadix + ((w >> (8 * q)) & 255u)], 1u);
+    }
+}
+
+template <typename KeyT>
+__device__ __forceinline__ void hist_count_vec(uint32_t* s_hist, const uint4& v)
+{
+    hist_count_word<KeyT>(s_hist, v.x, 0);
+    hist_count_word<KeyT>(s_hist, v.y, 1);
+    hist_count_word<KeyT>(s_hist, v.z, 2);
+    hist_count_word<KeyT>(s_hist, v.w, 3);
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kHistThreads)
+global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ ghist)
+{
+    constexpr int PLACES = sizeof(KeyT);
+    constexpr int VEC = 16 / sizeof(KeyT);
+    __shared__ uint32_t s_hist[PLACES * kRadix];
+    for (int i = threadIdx.x; i < PLACES * kRadix; i += kHistThreads) s_hist[i] = 0;
+    __syncthreads();
+
+    const uint64_t nvec = n / VEC;
+    const uint4* __restrict__ vp = reinterpret_cast<const uint4*>(keys);
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kHistThreads;
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * kHistThreads + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 a = __ldcs(vp + i);
+        const uint4 b = __ldcs(vp + i + stride);
+        const uint4 c = __ldcs(vp + i + 2 * stride);
+        const uint4 d = __ldcs(vp + i + 3 * stride);
+        hist_count_vec<KeyT>(s_hist, a);
+        hist_count_vec<KeyT>(s_hist, b);
+        hist_count_vec<KeyT>(s_hist, c);
+        hist_count_vec<KeyT>(s_hist, d);
+    }
+    for (; i < nvec; i += stride) {
+        const uint4 a = __ldcs(vp + i);
+        hist_count_vec<KeyT>(s_hist, a);
+    }
+    // ragged tail (n not a multiple of the vector width)
+    if (blockIdx.x == 0) {
+        const uint64_t t = nvec * VEC + threadIdx.x;
+        if (t < n) {
+            const KeyT k = keys[t];
+#pragma unroll
+            for (int p = 0; p < PLACES; ++p)
+                atomicAdd(&s_hist[p * kRadix + (static_cast<uint32_t>(k >> (8 * p)) & 255u)], 1u);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < PLACES * kRadix; j += kHistThreads) {
+        const uint32_t v = s_hist[j];
+        if (v) atomicAdd(&ghist[j], static_cast<unsigned long long>(v));
+    }
+}
+
+cudaError_t launch_global_histogram(const void* keys, uint64_t n, int key_bytes, unsigned long long* ghist,
+                                    int sm_count, cudaStream_t stream)
+{
+    const uint64_t vecs = n / (16 / key_bytes);
+    uint64_t want = (vecs + kHistThreads - 1) / kHistThreads;
+    if (want < 1) want = 1;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * kHistCtasPerSm;
+    const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+    if (key_bytes == 4)
+        global_histogram_kernel<uint32_t><<<grid, kHistThreads, 0, stream>>>(static_cast<const uint32_t*>(keys), n, ghist);
+    else
+        global_histogram_kernel<uint64_t><<<grid, kHistThreads, 0, stream>>>(static_cast<const uint64_t*>(keys), n, ghist);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Scan: exclusive prefix over the 256 bins of each digit place
+// =====================================================================================================
+__global__ void __launch_bounds__(kRadix)
+scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ gbase)
+{
+    __shared__ unsigned long long s_warp[kRadix / 32];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    const unsigned long long c = ghist[blockIdx.x * kRadix + d];
+    unsigned long long incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long pre = 0;
+    for (int w = 0; w < warp; ++w) pre += s_warp[w];
+    gbase[blockIdx.x * kRadix + d] = pre + incl - c;
+}
+
+cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream)
+{
+    scan_kernel<<<places, kRadix, 0, stream>>>(ghist, gbase);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Shared pieces of the digit-binning kernels
+// =====================================================================================================
+
+// 8-ballot warp match (RankMode::kRankBallot): mask of lanes holding the same digit.
+__device__ __forceinline__ uint32_t warp_match_digit(uint32_t d)
+{
+    uint32_t m = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < kRadixLog; ++b) {
+        const bool p = (d >> b) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, p);
+        m &= p ? bal : ~bal;
+    }
+    return m;
+}
+
+// Rank of one key per lane inside its warp's running histogram (returns #earlier keys of this warp with the
+// same digit, in tile order) and bumps the histogram.  `wh` = this warp's 256-bin histogram in shared memory.
+template <int RANK_MODE>
+__device__ __forceinline__ uint32_t warp_rank_and_count(uint32_t* wh, uint32_t d, uint32_t lt_mask)
+{
+    if constexpr (RANK_MODE == kRankAtomic) {
+        (void)lt_mask;
+        return atomicAdd(&wh[d], 1u);  // lane-ordered among same-digit lanes of this instruction (see header)
+    } else {
+        const uint32_t m = warp_match_digit(d);
+        const uint32_t below = __popc(m & lt_mask);
+        uint32_t pre = 0;
+        if (below == 0) { pre = wh[d]; wh[d] = pre + __popc(m); }
+        __syncwarp();
+        pre = __shfl_sync(0xffffffffu, pre, __ffs(m) - 1);
+        return pre + below;
+    }
+}
+
+// Exclusive scan of one value per digit thread (threads 0..255 contribute, all THREADS threads call).
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t c, uint32_t* s_wtot /*[8]*/)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (tid < kRadix && lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    uint32_t pre = 0;
+    if (tid < kRadix) {
+#pragma unroll
+        for (int w = 0; w < kRadix / 32; ++w) pre += (w < warp) ? s_wtot[w] : 0u;
+    }
+    return pre + incl - c;
+}
+
+// Decoupled lookback for (tile, digit d): sum of the digit counts of all predecessor tiles plus the global
+// digit base.  Reference: OneSweep.cu:306-327.  `tile_count` is this tile's count of digit d.
+__device__ __forceinline__ unsigned long long
+lookback_and_publish(uint64_t* desc, uint32_t tile, uint32_t d, uint32_t tile_count, uint32_t epoch,
+                     const unsigned long long* __restrict__ gbase)
+{
+    uint64_t* mine = desc + static_cast<uint64_t>(tile) * kRadix + d;
+    unsigned long long excl = 0;
+    int64_t k = static_cast<int64_t>(tile) - 1;
+    while (true) {
+        if (k < 0) { excl += gbase[d]; break; }
+        const uint64_t v = ld_relaxed_gpu_u64(desc + static_cast<uint64_t>(k) * kRadix + d);
+        const uint64_t flag = v & kFlagMask;
+        if (desc_epoch(v) != epoch || flag == kFlagNotReady) { __nanosleep(20); continue; }
+        excl += desc_value(v);
+        if (flag == kFlagInclusive) break;
+        --k;
+    }
+    st_relaxed_gpu_u64(mine, desc_pack(epoch, kFlagInclusive, excl + tile_count));
+    return excl;
+}
+
+// =====================================================================================================
+// DigitBinningPass, variant 0: one CTA per partition tile (dynamic tile id), keys held in registers.
+// =====================================================================================================
+template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE>
+__global__ void __launch_bounds__(WARPS * 32, (RANK_MODE == kRankAtomic && !PAIRS) ? 2 : 1)
+digit_binning_tile_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, const uint32_t* __restrict__ in_val,
+                          uint32_t* __restrict__ out_val, uint64_t n, uint32_t shift,
+                          const unsigned long long* __restrict__ gbase, uint64_t* desc, uint32_t* ticket, uint32_t epoch)
+{
+    constexpr int THREADS = WARPS * 32;
+    constexpr int T = THREADS * K;  // keys per partition tile
+    static_assert(WARPS >= 8, "need one thread per digit");
+    extern __shared__ __align__(16) unsigned char s_raw[];  // max(WARPS*256*4, T*sizeof(KeyT)) bytes
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_raw);  // [WARPS][256] during ranking
+    KeyT* s_keys = reinterpret_cast<KeyT*>(s_raw);          // [T] digit-sorted tile afterwards
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_raw);  // [T] payloads in the same order (pairs)
+    __shared__ unsigned long long s_keyptr[kRadix];  // per digit: byte address of out[global_base - tile_base]
+    __shared__ unsigned long long s_valptr[PAIRS ? kRadix : 1];
+    __shared__ uint32_t s_wtot[kRadix / 32];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < WARPS * kRadix; i += THREADS) s_hist[i] = 0;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);  // dynamic tile id: predecessors are already scheduled
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
+    const uint32_t valid = static_cast<uint32_t>(n - tile_base < static_cast<uint64_t>(T) ? n - tile_base : T);
+
+    // ---- load: warp-striped, one coalesced 128 B (256 B for u64) row per warp instruction --------------
+    KeyT key[K];
+    const uint32_t warp_off = warp * (32 * K) + lane;
+    if (valid == T) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) key[i] = ld_stream(in + tile_base + warp_off + i * 32);
+    } else {
+        // the last tile is padded with all-ones keys: they rank after every real key of digit 255 and
+        // therefore land at tile positions >= valid, which are never written (reference: OneSweep.cu:195-205)
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const uint32_t idx = warp_off + i * 32;
+            key[i] = idx < valid ? in[tile_base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));
+        }
+    }
+
+    // ---- rank inside the warp (tile order = warp-major, then round, then lane) ------------------------
+    uint32_t off[K];
+    uint32_t* wh = s_hist + warp * kRadix;
+    const uint32_t lt = lanemask_lt();
+#pragma unroll
+    for (int i = 0; i < K; ++i) off[i] = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
+    __syncthreads();
+
+    // ---- per digit: exclusive prefix over the warps, tile reduction, publish, scan over digits --------
+    uint32_t tile_count = 0, tile_excl = 0;
+    {
+        uint32_t wcount[WARPS];
+        if (tid < kRadix) {
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { wcount[w] = s_hist[w * kRadix + tid]; tile_count += wcount[w]; }
+            st_relaxed_gpu_u64(desc + static_cast<uint64_t>(tile) * kRadix + tid,
+                               desc_pack(epoch, kFlagReduction, tile_count));
+        }
+        tile_excl = block_excl_scan_256<THREADS>(tile_count, s_wtot);
+        if (tid < kRadix) {
+            uint32_t run = tile_excl;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { s_hist[w * kRadix + tid] = run; run += wcount[w]; }
+        }
+    }
+    __syncthreads();
+
+    // ---- position of every key inside the digit-sorted tile -------------------------------------------
+#pragma unroll
+    for (int i = 0; i < K; ++i) off[i] += wh[digit_of(key[i], shift)];
+    __syncthreads();  // histograms are dead; the same shared memory now receives the sorted tile
+
+#pragma unroll
+    for (int i = 0; i < K; ++i) s_keys[off[i]] = key[i];
+
+    // payload loads are issued here so that their latency overlaps the lookback
+    uint32_t val[PAIRS ? K : 1];
+    if constexpr (PAIRS) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const uint32_t idx = warp_off + i * 32;
+            val[i] = idx < valid ? ld_stream(in_val + tile_base + idx) : 0u;
+        }
+    }
+
+    // ---- chained scan with decoupled lookback, one thread per digit -----------------------------------
+    if (tid < kRadix) {
+        const unsigned long long excl = lookback_and_publish(desc, tile, tid, tile_count, epoch, gbase);
+        const unsigned long long first = excl - tile_excl;  // out index of tile position 0 "as if" of this digit
+        s_keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
+        if constexpr (PAIRS) s_valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
+    }
+    __syncthreads();
+
+    // ---- scatter: consecutive threads write consecutive addresses inside each digit run ---------------
+    uint32_t dg[PAIRS ? K : 1];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        const uint32_t idx = j * THREADS + tid;
+        if (idx < valid) {
+            const KeyT k = s_keys[idx];
+            const uint32_t d = digit_of(k, shift);
+            if constexpr (PAIRS) dg[j] = d;
+            KeyT* dst = reinterpret_cast<KeyT*>(s_keyptr[d]) + idx;
+            st_stream(dst, k);
+        }
+    }
+    if constexpr (PAIRS) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < K; ++i) s_vals[off[i]] = val[i];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            if (idx < valid) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(s_valptr[dg[j]]) + idx;
+                st_stream(dst, s_vals[idx]);
+            }
+        }
+    }
+}
+
+// ---- variant-0 geometry ------------------------------------------------------------------------------
+template <typename KeyT, bool PAIRS> struct TileGeom;
+template <> struct TileGeom<uint32_t, false> { static constexpr int K = 16, WARPS = 16; };
+template <> struct TileGeom<uint32_t, true>  { static constexpr int K = 16, WARPS = 16; };
+template <> struct TileGeom<uint64_t, false> { static constexpr int K = 8,  WARPS = 16; };
+
+template <typename KeyT, bool PAIRS>
+constexpr size_t tile_smem_bytes()
+{
+    using G = TileGeom<KeyT, PAIRS>;
+    const size_t hist = static_cast<size_t>(G::WARPS) * kRadix * 4;
+    const size_t keys = static_cast<size_t>(G::WARPS) * 32 * G::K * sizeof(KeyT);
+    return hist > keys ? hist : keys;
+}
+
+template <typename KeyT, bool PAIRS, int RANK_MODE>
+static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
+                                       uint32_t shift, const unsigned long long* gbase, uint64_t* desc, uint32_t* ticket,
+                                       uint32_t epoch, cudaStream_t stream)
+{
+    using G = TileGeom<KeyT, PAIRS>;
+    constexpr int T = G::WARPS * 32 * G::K;
+    const uint64_t tiles = (n + T - 1) / T;
+    auto kern = digit_binning_tile_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE>;
+    kern<<<static_cast<unsigned>(tiles), G::WARPS * 32, tile_smem_bytes<KeyT, PAIRS>(), stream>>>(
+        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, desc, ticket, epoch);
+    return cudaGetLastError();
+}
+
+uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
+{
+    (void)cfg;
+    if (key_bytes == 8) return TileGeom<uint64_t, false>::WARPS * 32 * TileGeom<uint64_t, false>::K;
+    if (pairs) return TileGeom<uint32_t, true>::WARPS * 32 * TileGeom<uint32_t, true>::K;
+    return TileGeom<uint32_t, false>::WARPS * 32 * TileGeom<uint32_t, false>::K;
+}
+
+template <typename KeyT, bool PAIRS, int RANK_MODE>
+static cudaError_t set_tile_attr()
+{
+    using G = TileGeom<KeyT, PAIRS>;
+    return cudaFuncSetAttribute(digit_binning_tile_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(tile_smem_bytes<KeyT, PAIRS>()));
+}
+
+cudaError_t configure_kernels()
+{
+    cudaError_t e;
+    if ((e = set_tile_attr<uint32_t, false, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_tile_attr<uint32_t, false, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_tile_attr<uint32_t, true, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_tile_attr<uint32_t, true, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_tile_attr<uint64_t, false, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_tile_attr<uint64_t, false, kRankBallot>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
+                                 int key_bytes, uint32_t shift, const unsigned long long* gbase_place, uint64_t* desc,
+                                 uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg, cudaStream_t stream)
+{
+    const bool pairs = in_val != nullptr;
+    const bool ballot = cfg.rank_mode == kRankBallot;
+#define OSB_DISPATCH(KEYT, PAIRS)                                                                                   \
+    (ballot ? launch_tile_variant<KEYT, PAIRS, kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, desc,  \
+                                                           ticket, epoch, stream)                                   \
+            : launch_tile_variant<KEYT, PAIRS, kRankAtomic>(in, out, in_val, out_val, n, shift, gbase_place, desc,  \
+                                                           ticket, epoch, stream))
+    if (key_bytes == 4) return pairs ? OSB_DISPATCH(uint32_t, true) : OSB_DISPATCH(uint32_t, false);
+    if (key_bytes == 8 && !pairs) return OSB_DISPATCH(uint64_t, false);
+#undef OSB_DISPATCH
+    return cudaErrorInvalidValue;
+}
+
+// =====================================================================================================
+// Validate: adjacent-inversion count (reference: UtilityKernels.cuh:403-429)
+// =====================================================================================================
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+validate_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* err_count)
+{
+    unsigned long long bad = 0;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i + 1 < n; i += stride)
+        bad += keys[i] > keys[i + 1];
+    for (int o = 16; o > 0; o >>= 1) bad += __shfl_down_sync(0xffffffffu, bad, o);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(err_count, bad);
+}
+
+cudaError_t launch_validate(const void* keys, uint64_t n, int key_bytes, unsigned long long* err_count, int sm_count,
+                            cudaStream_t stream)
+{
+    const unsigned grid = static_cast<unsigned>(sm_count) * 8;
+    if (key_bytes == 4) validate_kernel<uint32_t><<<grid, 256, 0, stream>>>(static_cast<const uint32_t*>(keys), n, err_count);
+    else validate_kernel<uint64_t><<<grid, 256, 0, stream>>>(static_cast<const uint64_t*>(keys), n, err_count);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// InitRandom: the reference's input generator (UtilityKernels.cuh:26-33,53-117), restated from its
+// published recurrences (hybrid Tausworthe + LCG, GPU Gems 3 ch. 37).  Test/bench utility, not on the hot path.
+// =====================================================================================================
+constexpr uint32_t kGenStreams = 65536;
+
+struct HybridTaus {
+    uint32_t a, b, c, l;
+    __device__ __forceinline__ uint32_t next()
+    {
+        a = ((a & 0xfffffffeu) << 12) ^ (((a << 13) ^ a) >> 19);
+        b = ((b & 0xfffffff8u) << 4) ^ (((b << 2) ^ b) >> 25);
+        c = ((c & 0xfffffff0u) << 17) ^ (((c << 3) ^ c) >> 11);
+        l = l * 1664525u + 1013904223u;
+        return a ^ b ^ c ^ l;
+    }
+};
+
+__global__ void __launch_bounds__(256)
+init_random_kernel(uint32_t* __restrict__ keys, uint32_t* __restrict__ payload, uint64_t n, uint32_t and_count,
+                   uint32_t seed, bool payload_is_index)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;  // stream id, 0..65535
+    HybridTaus s{(g * 4u) * seed, (g * 4u + 1u) * seed, (g * 4u + 2u) * seed, (g * 4u + 3u) * seed};
+    (void)s.next();  // one warm-up step
+    for (uint64_t i = g; i < n; i += kGenStreams) {
+        uint32_t t = 0xffffffffu;
+        for (uint32_t k = 0; k <= and_count; ++k) t &= s.next();
+        keys[i] = t;
+        if (payload) payload[i] = payload_is_index ? static_cast<uint32_t>(i) : t;
+    }
+}
+
+cudaError_t launch_init_random(uint32_t* keys, uint32_t* payload, uint64_t n, uint32_t and_count, uint32_t seed,
+                               bool payload_is_index, cudaStream_t stream)
+{
+    init_random_kernel<<<kGenStreams / 256, 256, 0, stream>>>(keys, payload, n, and_count, seed, payload_is_index);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Self-test of the hardware property RankMode::kRankAtomic relies on
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+atomic_order_selftest_kernel(unsigned long long* mismatches)
+{
+    __shared__ uint32_t s_hist[8 * kRadix];
+    __shared__ uint32_t s_ref[8 * kRadix];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* wh = s_hist + warp * kRadix;
+    uint32_t* wr = s_ref + warp * kRadix;
+    uint32_t s = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    const uint32_t lt = lanemask_lt();
+    unsigned long long bad = 0;
+    for (int it = 0; it < 24; ++it) {
+        for (int i = lane; i < kRadix; i += 32) { wh[i] = 0; wr[i] = 0; }
+        __syncwarp();
+        for (int i = 0; i < 16; ++i) {
+            uint32_t d = 255u;
+            const int draws = 1 + (it % 6);  // entropy sweep: uniform digits down to heavy collisions
+            for (int k = 0; k < draws; ++k) { s = s * 1664525u + 1013904223u; d &= (s >> 13); }
+            if (it % 6 == 5) d = (it + i) & 255u;  // every lane the same digit
+            const uint32_t got = warp_rank_and_count<kRankAtomic>(wh, d, lt);
+            const uint32_t want = warp_rank_and_count<kRankBallot>(wr, d, lt);
+            bad += (got != want);
+            __syncwarp();
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+cudaError_t launch_atomic_order_selftest(unsigned long long* mismatches, int sm_count, cudaStream_t stream)
+{
+    atomic_order_selftest_kernel<<<sm_count * 2, 256, 0, stream>>>(mismatches);
+    return cudaGetLastError();
+}
+
+}  // namespace osb

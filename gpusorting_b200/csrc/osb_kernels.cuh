@@ -1,0 +1,62 @@
+// osb_kernels.cuh -- launch interface of the sm_100a OneSweep kernels (implemented in osb_kernels.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace osb {
+
+// Kernel variants of the digit-binning pass (osb200_set_option "variant").
+enum BinningVariant : int {
+    kVariantTilePerCta = 0,  // one CTA per partition tile, keys loaded straight into registers
+    kVariantPersistent = 1,  // persistent CTAs, TMA (cp.async.bulk) double-buffered tile staging
+};
+enum RankMode : int {
+    kRankAtomic = 0,  // one shared-memory atomicAdd per key (lane-ordered on sm_100, verified at create)
+    kRankBallot = 1,  // 8 ballots per key (the reference's warp-level multisplit, OneSweep.cu:208-253)
+};
+
+struct BinningConfig {
+    int variant = kVariantTilePerCta;
+    int rank_mode = kRankAtomic;
+    int sm_count = 148;
+};
+
+// keys per partition tile for a key width / pairs flag / variant (host needs it to size descriptors)
+uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg);
+
+// One-time per-process kernel attribute setup (dynamic shared memory opt-in). Returns cudaError_t.
+cudaError_t configure_kernels();
+
+// GlobalHistogram (reference: OneSweep::GlobalHistogram, Sort/OneSweep.cu:44-123).
+// ghist[place*256 + digit] += counts; caller zeroes ghist first.
+cudaError_t launch_global_histogram(const void* keys, uint64_t n, int key_bytes, unsigned long long* ghist,
+                                    int sm_count, cudaStream_t stream);
+
+// Scan (reference: OneSweep::Scan, Sort/OneSweep.cu:125-162): per place exclusive prefix of ghist -> gbase.
+cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream);
+
+// DigitBinningPass (reference: OneSweep::DigitBinningPassKeysOnly / Pairs, Sort/OneSweep.cu:164-600).
+//   gbase_place: [256] exclusive global digit bases for this digit place
+//   desc:        [tiles][256] 64-bit tile descriptors (never cleared; `epoch` distinguishes launches)
+//   ticket:      one zeroed u32 (dynamic tile id counter, reference `index[]`)
+cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
+                                 int key_bytes, uint32_t shift, const unsigned long long* gbase_place, uint64_t* desc,
+                                 uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg, cudaStream_t stream);
+
+// Validate (reference: Validate, UtilityKernels.cuh:403-429): err_count += #(keys[i] > keys[i+1]).
+cudaError_t launch_validate(const void* keys, uint64_t n, int key_bytes, unsigned long long* err_count, int sm_count,
+                            cudaStream_t stream);
+
+// InitRandom (reference: InitRandom, UtilityKernels.cuh:53-117, launched <<<256,256>>> by
+// OneSweepDispatcher.cuh:100-104): the reference's deterministic test-input generator.  65,536 hybrid
+// Tausworthe/LCG streams; stream g writes elements g, g+65536, ...; each element ANDs and_count+1 draws.
+// payload (may be null) receives a copy of the key (reference pairs overload) or, if payload_is_index, i.
+cudaError_t launch_init_random(uint32_t* keys, uint32_t* payload, uint64_t n, uint32_t and_count, uint32_t seed,
+                               bool payload_is_index, cudaStream_t stream);
+
+// Device self-test: does a shared-memory atomicAdd hand out its return values in ascending lane order among
+// the lanes of one warp instruction that hit the same address?  (kRankAtomic depends on it.)
+// mismatches (device u64) receives the number of violations found.
+cudaError_t launch_atomic_order_selftest(unsigned long long* mismatches, int sm_count, cudaStream_t stream);
+
+}  // namespace osb

@@ -1,0 +1,155 @@
+/*
+ * onesweep_b200.h -- C-ABI of the B200-native OneSweep radix sort (libonesweep_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of b0nes164/GPUSorting that this repository
+ * rebuilds: the CUDA OneSweep 8-bit LSD radix sort.  Plain C types only (no torch / C++ types).
+ * Each entry point cites the reference interface it replaces; paths are relative to
+ * /root/reference/GPUSortingCUDA/ unless stated otherwise.
+ *
+ * Conventions
+ *   - All `d_*` pointers are device pointers on the handle's device; keys must be 16-byte aligned
+ *     (the reference assumes this too: Sort/OneSweep.cu:77 reinterpret_cast<uint4*>).
+ *   - The sorted result is returned IN the caller's key/value buffers (even number of passes, like
+ *     Sort/OneSweepDispatcher.cuh:325-335 which ends in m_sort).
+ *   - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default stream) and
+ *     never synchronise the host, unlike the reference (cudaDeviceSynchronize inside the dispatch,
+ *     OneSweepDispatcher.cuh:318).  One sort in flight per handle; distinct handles are independent.
+ *   - Return value: 0 on success, a negative osb200_status otherwise.  Nothing aborts or prints (the
+ *     reference ignores every CUDA error and printf()s on misuse, OneSweepDispatcher.cuh:195-199).
+ *   - n == 0 or 1 is a successful no-op; n > max_n (from create) is OSB200_ERR_SIZE.
+ *   - There is NO CPU fallback: if no sm_100 device / driver is usable, create fails.
+ */
+#ifndef ONESWEEP_B200_H_
+#define ONESWEEP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(OSB200_BUILDING) && defined(__GNUC__)
+#define OSB200_API __attribute__((visibility("default")))
+#else
+#define OSB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct osb200_sorter* osb200_handle;          /* opaque single-GPU sorter  */
+typedef struct osb200_sharded_sorter* osb200_sharded_handle; /* opaque multi-GPU sorter */
+
+typedef enum osb200_status {
+    OSB200_OK = 0,
+    OSB200_ERR_INVALID_ARG = -1, /* null handle/pointer, bad key/value width, misaligned keys    */
+    OSB200_ERR_SIZE = -2,        /* n > max_n of the handle                                        */
+    OSB200_ERR_UNSUPPORTED = -3, /* combination not built (e.g. u64 keys with values)              */
+    OSB200_ERR_NO_DEVICE = -4,   /* no CUDA device of compute capability 10.x                      */
+    OSB200_ERR_ALLOC = -5,       /* device allocation failed                                       */
+    OSB200_ERR_NCCL = -6,        /* NCCL failure in the sharded path                               */
+    OSB200_ERR_CUDA = -1000      /* -(1000 + cudaError_t) for any other CUDA runtime error         */
+} osb200_status;
+
+/* ABI version of this header (major*1000 + minor). */
+OSB200_API int osb200_version(void);
+/* Static string for a status code returned by any function below. */
+OSB200_API const char* osb200_status_string(int status);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sorter object.  Replaces  OneSweepDispatcher::OneSweepDispatcher(bool keysOnly, uint32_t maxSize)
+ * / ~OneSweepDispatcher()  (Sort/OneSweepDispatcher.cuh:42-83): owns the alternate (ping-pong)
+ * buffers, the global histogram, the tile tickets and the chained-scan tile descriptors.  Unlike the
+ * reference the caller owns the keys/values being sorted (as in the Unity API,
+ * /root/reference/GPUSortingUnity/Runtime/OneSweep.cs:297-306).
+ *   key_bytes   4 (uint32 keys, the reference's only CUDA type) or 8 (uint64 keys, 8 digit passes)
+ *   value_bytes 0 (keys only == keysOnly=true) or 4 (uint32 payload == keysOnly=false)
+ *   max_n       largest n a sort call may pass (reference: maxSize), up to 2^34
+ * The device is the calling thread's current CUDA device.
+ * ---------------------------------------------------------------------------------------------- */
+OSB200_API int osb200_create(osb200_handle* out, uint64_t max_n, int key_bytes, int value_bytes);
+OSB200_API int osb200_destroy(osb200_handle h);
+/* Device bytes a handle with these parameters allocates (alt buffers + control state). */
+OSB200_API uint64_t osb200_workspace_bytes(uint64_t max_n, int key_bytes, int value_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sort entry points.
+ *   osb200_sort_keys_u32      replaces OneSweepDispatcher::DispatchKernelsKeysOnly(uint32_t size)
+ *                             (Sort/OneSweepDispatcher.cuh:311-336)
+ *   osb200_sort_pairs_u32     replaces OneSweepDispatcher::DispatchKernelsPairs(uint32_t size)
+ *                             (Sort/OneSweepDispatcher.cuh:338-363); stable: equal keys keep their
+ *                             input order (in-order ranking, Sort/OneSweep.cu:207-253)
+ *   osb200_sort_keys_u64      no CUDA reference; same plan with 8 digit places, shape of
+ *                             GPUSortingUnity/Runtime/OneSweep.cs:297-306 Sort(...)
+ * ---------------------------------------------------------------------------------------------- */
+OSB200_API int osb200_sort_keys_u32(osb200_handle h, uint32_t* d_keys, uint64_t n, void* stream);
+OSB200_API int osb200_sort_pairs_u32(osb200_handle h, uint32_t* d_keys, uint32_t* d_values, uint64_t n, void* stream);
+OSB200_API int osb200_sort_keys_u64(osb200_handle h, uint64_t* d_keys, uint64_t n, void* stream);
+
+/* Host-buffer entry points: copy in, sort, copy back, synchronise.  `h_*` may be pageable or pinned
+ * host memory.  This is the end-to-end call a host-side caller of the reference would make (the
+ * reference itself has no host-data API; its buffers are generated on the device,
+ * OneSweepDispatcher.cuh:215-219). */
+OSB200_API int osb200_sort_host_keys_u32(osb200_handle h, uint32_t* h_keys, uint64_t n);
+OSB200_API int osb200_sort_host_pairs_u32(osb200_handle h, uint32_t* h_keys, uint32_t* h_values, uint64_t n);
+OSB200_API int osb200_sort_host_keys_u64(osb200_handle h, uint64_t* h_keys, uint64_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Kernel-level entry points (for parity tests against the reference's individual kernels).
+ *   osb200_global_histogram   replaces OneSweep::GlobalHistogram<<<...>>> (Sort/OneSweep.cu:44-123):
+ *                             d_hist[place*256 + digit], uint64 counts, key_bytes places, overwritten.
+ *   osb200_digit_binning_pass replaces OneSweep::Scan + one OneSweep::DigitBinningPassKeysOnly/Pairs
+ *                             launch (Sort/OneSweep.cu:125-162,164-344,346-600): a stable counting
+ *                             sort of d_in (and d_in_values, may be NULL) on the 8-bit digit at
+ *                             `radix_shift` into d_out (d_out_values).  Out-of-place.
+ *   osb200_validate           replaces Validate<<<...>>> (UtilityKernels.cuh:403-429,432-479):
+ *                             *h_err_count = number of adjacent inversions in d_keys (synchronises).
+ * ---------------------------------------------------------------------------------------------- */
+OSB200_API int osb200_global_histogram(osb200_handle h, const void* d_keys, uint64_t n, uint64_t* d_hist, void* stream);
+OSB200_API int osb200_digit_binning_pass(osb200_handle h, const void* d_in, void* d_out, const uint32_t* d_in_values,
+                              uint32_t* d_out_values, uint64_t n, uint32_t radix_shift, void* stream);
+OSB200_API int osb200_validate(osb200_handle h, const void* d_keys, uint64_t n, uint64_t* h_err_count, void* stream);
+
+/* Test-input generator.  Replaces InitRandom<<<256,256>>> (UtilityKernels.cuh:53-83 keys, :85-117 pairs):
+ * the reference's deterministic hybrid Tausworthe/LCG generator with Thearling-Smith entropy reduction
+ * (and_count = ENTROPY_PRESET value 0..4).  d_payload may be NULL; if not, it receives a copy of the key
+ * (reference behaviour, UtilityKernels.cuh:115) or the element index when payload_is_index != 0 (stricter
+ * stability test).  The whole 64-bit n is honoured (the reference takes uint32 size). */
+OSB200_API int osb200_init_random_u32(uint32_t* d_keys, uint32_t* d_payload, uint64_t n, uint32_t and_count, uint32_t seed,
+                           int payload_is_index, void* stream);
+
+/* Tuning / introspection (no reference equivalent; the reference's constants are #defines,
+ * Sort/OneSweep.cu:17-42).  Keys: "rank_mode" 0=atomic-ranked (default) 1=ballot-ranked;
+ * "variant" kernel variant id; returns OSB200_ERR_INVALID_ARG for unknown keys/values. */
+OSB200_API int osb200_set_option(osb200_handle h, const char* key, int64_t value);
+OSB200_API int64_t osb200_get_info(osb200_handle h, const char* key); /* "tile_keys","launches_per_sort","sm_count",... ; <0 if unknown */
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU sharded sort (one process per GPU).  No reference equivalent (the reference is single
+ * device); this is BASELINE.json's "MSD bucket-exchange then local OneSweep".
+ *
+ *   osb200_sharded_unique_id  rank 0 fills a 128-byte NCCL unique id; the host application broadcasts
+ *                             it to all ranks (torch.distributed / MPI / files).
+ *   osb200_sharded_create     every rank: joins the communicator (world ranks on ONE node), allocates
+ *                             receive + local-sort workspace for up to max_n_local keys per rank plus
+ *                             `slack_percent` head-room for bucket imbalance.
+ *   osb200_sharded_sort_keys_u32
+ *                             every rank passes its n_local unsorted keys.  After the call rank r owns
+ *                             the r-th contiguous slice of the global ascending order: *d_out points
+ *                             into handle-owned memory valid until the next call, *n_out is its length.
+ *                             Steps: local top-digit histogram -> all-gather of the 256-bin histograms
+ *                             -> bucket->rank assignment -> exchange pass (keys move over NVLink) ->
+ *                             local OneSweep.
+ * ---------------------------------------------------------------------------------------------- */
+OSB200_API int osb200_sharded_unique_id(void* out_128_bytes);
+OSB200_API int osb200_sharded_create(osb200_sharded_handle* out, const void* unique_id_128_bytes, int rank, int world,
+                          uint64_t max_n_local, int slack_percent);
+OSB200_API int osb200_sharded_destroy(osb200_sharded_handle h);
+OSB200_API int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys_local, uint64_t n_local,
+                                 uint32_t** d_out, uint64_t* n_out, void* stream);
+/* Milliseconds of the phases of the last sharded sort on this rank: [0]=histogram+allgather,
+ * [1]=exchange, [2]=local sort, [3]=total (device time, CUDA events). */
+OSB200_API int osb200_sharded_last_timing(osb200_sharded_handle h, float* out_ms4);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* ONESWEEP_B200_H_ */

@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from tests import oraclelib
+
+    return oraclelib.load_oracle()
+
+
+@pytest.fixture(scope="session")
+def reflib():
+    """The reference's own CUDA kernels (oracle/_ref/libref_onesweep.so), or None if it was not built."""
+    from tests import oraclelib
+
+    return oraclelib.load_ref()

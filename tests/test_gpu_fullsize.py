@@ -1,0 +1,84 @@
+"""BASELINE.json's full sizes (2^30) through size-independent properties: sortedness (the reference's Validate),
+conservation of every digit-place histogram, a multiset checksum, stability via payload order, and -- when
+oracle/_ref exists -- bit-exact equality with the reference's CUDA OneSweep.  Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def multiset_checksum(t):
+    # order-independent: wrapping sum and xor of all elements
+    x = t.view(torch.int32).to(torch.int64)
+    return int(x.sum().item()), int(torch.bitwise_xor(x[::2][: x.numel() // 2], x[1::2][: x.numel() // 2]).sum().item())
+
+
+@pytest.fixture(scope="module")
+def g():
+    import gpusorting_b200 as g
+
+    return g
+
+
+def test_keys_u32_2pow30(g, reflib):
+    n = 1 << 30
+    s = g.OneSweepSorter(n, 4, 0)
+    t = torch.empty(n, dtype=torch.int32, device="cuda")
+    g.init_random(t, 0, 10)
+    h0 = s.global_histogram(t).clone()
+    c0 = multiset_checksum(t)
+    ref_out = None
+    if reflib is not None:  # the reference is valid up to exactly 2^30 (30-bit descriptor value)
+        h = reflib.lib.ref_create(n)
+        a, alt = t.clone(), torch.empty_like(t)
+        assert reflib.lib.ref_sort_keys(h, a.data_ptr(), alt.data_ptr(), n) == 0
+        torch.cuda.synchronize()
+        del alt
+        ref_out = a
+        reflib.lib.ref_destroy(h)
+    s.sort_keys(t)
+    assert s.validate(t) == 0
+    assert torch.equal(s.global_histogram(t), h0)
+    assert multiset_checksum(t) == c0
+    if ref_out is not None:
+        assert torch.equal(t, ref_out)
+    # idempotence: sorting sorted data changes nothing
+    first = t[: 1 << 20].clone()
+    s.sort_keys(t)
+    assert torch.equal(t[: 1 << 20], first) and s.validate(t) == 0
+    s.close()
+
+
+def test_pairs_u32_2pow30_stability(g):
+    n = 1 << 30
+    s = g.OneSweepSorter(n, 4, 4)
+    k = torch.empty(n, dtype=torch.int32, device="cuda")
+    v = torch.empty(n, dtype=torch.int32, device="cuda")
+    g.init_random(k, 0, 10, payload=v, payload_is_index=True)
+    k &= 0xFFFFF  # ~1024 duplicates per key value: stability is observable
+    kin = k.clone()
+    s.sort_pairs(k, v)
+    assert s.validate(k) == 0
+    # payload round trip: output key i must be the input key at index v[i]
+    idx = v.view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    assert torch.equal(kin[idx], k)
+    del kin, idx
+    # stability: inside every run of equal keys the original indices ascend
+    same = k[1:] == k[:-1]
+    vi = v.to(torch.int64) & 0xFFFFFFFF
+    assert bool(((vi[1:] > vi[:-1]) | ~same).all())
+    s.close()
+
+
+def test_keys_u64_2pow30(g):
+    n = 1 << 30
+    s = g.OneSweepSorter(n, 8, 0)
+    w = torch.empty(2 * n, dtype=torch.int32, device="cuda")
+    g.init_random(w, 0, 10)  # hi/lo words are consecutive draws of the reference generator
+    t = w.view(torch.int64)
+    h0 = s.global_histogram(t).clone()
+    s.sort_keys(t)
+    assert s.validate(t) == 0
+    assert torch.equal(s.global_histogram(t), h0)
+    s.close()
