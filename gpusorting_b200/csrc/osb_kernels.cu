@@ -19,40 +19,53 @@ namespace osb {
 
 // =====================================================================================================
 // GlobalHistogram
+//
+// One streaming read of the keys, counting all digit places at once (reference: OneSweep.cu:44-123).  At B200
+// bandwidth this kernel needs ~23 shared-memory atomic lanes per SM clock (5.8 u32 keys/clk/SM x 4 places), so
+// bank conflicts between the lanes of one ATOMS instruction are unaffordable.  The per-CTA histogram is therefore
+// laid out [place][digit][column] with column = lane (32 columns for u32 keys, 16 for u64): every lane of a warp
+// instruction hits its own bank, whatever the data.  128 KB of shared memory, one 1024-thread CTA per SM.
 // =====================================================================================================
-constexpr int kHistThreads = 512;
-constexpr int kHistCtasPerSm = 4;
+constexpr int kHistThreads = 1024;
+
+template <typename KeyT> struct HistGeom;
+template <> struct HistGeom<uint32_t> { static constexpr int COLS = 32; };
+template <> struct HistGeom<uint64_t> { static constexpr int COLS = 16; };
 
 template <typename KeyT>
-__device__ __forceinline__ void hist_count_word(uint32_t* s_hist, uint32_t w, int word_in_vec)
+__device__ __forceinline__ void hist_count_word(uint32_t* s_col, uint32_t w, int word_in_vec)
 {
     constexpr int PLACES = sizeof(KeyT);
+    constexpr int COLS = HistGeom<KeyT>::COLS;
     // byte q of 32-bit word `word_in_vec` of a 16-byte vector is digit place ((word*4+q) % PLACES) of some key
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int place = (word_in_vec * 4 + q) % PLACES;
-        atomicAdd(&s_hist[place * kRadix + ((w >> (8 * q)) & 255u)], 1u);
+        atomicAdd(&s_col[(place * kRadix + ((w >> (8 * q)) & 255u)) * COLS], 1u);
     }
 }
 
 template <typename KeyT>
-__device__ __forceinline__ void hist_count_vec(uint32_t* s_hist, const uint4& v)
+__device__ __forceinline__ void hist_count_vec(uint32_t* s_col, const uint4& v)
 {
-    hist_count_word<KeyT>(s_hist, v.x, 0);
-    hist_count_word<KeyT>(s_hist, v.y, 1);
-    hist_count_word<KeyT>(s_hist, v.z, 2);
-    hist_count_word<KeyT>(s_hist, v.w, 3);
+    hist_count_word<KeyT>(s_col, v.x, 0);
+    hist_count_word<KeyT>(s_col, v.y, 1);
+    hist_count_word<KeyT>(s_col, v.z, 2);
+    hist_count_word<KeyT>(s_col, v.w, 3);
 }
 
 template <typename KeyT>
-__global__ void __launch_bounds__(kHistThreads)
+__global__ void __launch_bounds__(kHistThreads, 1)
 global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ ghist)
 {
     constexpr int PLACES = sizeof(KeyT);
     constexpr int VEC = 16 / sizeof(KeyT);
-    __shared__ uint32_t s_hist[PLACES * kRadix];
-    for (int i = threadIdx.x; i < PLACES * kRadix; i += kHistThreads) s_hist[i] = 0;
+    constexpr int COLS = HistGeom<KeyT>::COLS;
+    constexpr int BINS = PLACES * kRadix;
+    extern __shared__ __align__(16) uint32_t s_hist[];  // [BINS][COLS]
+    for (int i = threadIdx.x; i < BINS * COLS; i += kHistThreads) s_hist[i] = 0;
     __syncthreads();
+    uint32_t* s_col = s_hist + (threadIdx.x & (COLS - 1));  // this lane's private column (bank)
 
     const uint64_t nvec = n / VEC;
     const uint4* __restrict__ vp = reinterpret_cast<const uint4*>(keys);
@@ -63,14 +76,14 @@ global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long
         const uint4 b = __ldcs(vp + i + stride);
         const uint4 c = __ldcs(vp + i + 2 * stride);
         const uint4 d = __ldcs(vp + i + 3 * stride);
-        hist_count_vec<KeyT>(s_hist, a);
-        hist_count_vec<KeyT>(s_hist, b);
-        hist_count_vec<KeyT>(s_hist, c);
-        hist_count_vec<KeyT>(s_hist, d);
+        hist_count_vec<KeyT>(s_col, a);
+        hist_count_vec<KeyT>(s_col, b);
+        hist_count_vec<KeyT>(s_col, c);
+        hist_count_vec<KeyT>(s_col, d);
     }
     for (; i < nvec; i += stride) {
         const uint4 a = __ldcs(vp + i);
-        hist_count_vec<KeyT>(s_hist, a);
+        hist_count_vec<KeyT>(s_col, a);
     }
     // ragged tail (n not a multiple of the vector width)
     if (blockIdx.x == 0) {
@@ -79,15 +92,20 @@ global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long
             const KeyT k = keys[t];
 #pragma unroll
             for (int p = 0; p < PLACES; ++p)
-                atomicAdd(&s_hist[p * kRadix + (static_cast<uint32_t>(k >> (8 * p)) & 255u)], 1u);
+                atomicAdd(&s_col[(p * kRadix + (static_cast<uint32_t>(k >> (8 * p)) & 255u)) * COLS], 1u);
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < PLACES * kRadix; j += kHistThreads) {
-        const uint32_t v = s_hist[j];
-        if (v) atomicAdd(&ghist[j], static_cast<unsigned long long>(v));
+    // fold the columns (rotated start so the 32 lanes of a warp read 32 different banks)
+    for (int bin = threadIdx.x; bin < BINS; bin += kHistThreads) {
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (int c = 0; c < COLS; ++c) sum += s_hist[bin * COLS + ((c + threadIdx.x) & (COLS - 1))];
+        if (sum) atomicAdd(&ghist[bin], static_cast<unsigned long long>(sum));
     }
 }
+
+template <typename KeyT> constexpr size_t hist_smem_bytes() { return sizeof(KeyT) * kRadix * HistGeom<KeyT>::COLS * sizeof(uint32_t); }
 
 cudaError_t launch_global_histogram(const void* keys, uint64_t n, int key_bytes, unsigned long long* ghist,
                                     int sm_count, cudaStream_t stream)
@@ -95,12 +113,13 @@ cudaError_t launch_global_histogram(const void* keys, uint64_t n, int key_bytes,
     const uint64_t vecs = n / (16 / key_bytes);
     uint64_t want = (vecs + kHistThreads - 1) / kHistThreads;
     if (want < 1) want = 1;
-    const uint64_t cap = static_cast<uint64_t>(sm_count) * kHistCtasPerSm;
-    const unsigned grid = static_cast<unsigned>(want < cap ? want : cap);
+    const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) ? want : sm_count);
     if (key_bytes == 4)
-        global_histogram_kernel<uint32_t><<<grid, kHistThreads, 0, stream>>>(static_cast<const uint32_t*>(keys), n, ghist);
+        global_histogram_kernel<uint32_t><<<grid, kHistThreads, hist_smem_bytes<uint32_t>(), stream>>>(
+            static_cast<const uint32_t*>(keys), n, ghist);
     else
-        global_histogram_kernel<uint64_t><<<grid, kHistThreads, 0, stream>>>(static_cast<const uint64_t*>(keys), n, ghist);
+        global_histogram_kernel<uint64_t><<<grid, kHistThreads, hist_smem_bytes<uint64_t>(), stream>>>(
+            static_cast<const uint64_t*>(keys), n, ghist);
     return cudaGetLastError();
 }
 
@@ -268,10 +287,9 @@ digit_binning_tile_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     // ---- per digit: exclusive prefix over the warps, tile reduction, publish, scan over digits --------
     uint32_t tile_count = 0, tile_excl = 0;
     {
-        uint32_t wcount[WARPS];
         if (tid < kRadix) {
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) { wcount[w] = s_hist[w * kRadix + tid]; tile_count += wcount[w]; }
+            for (int w = 0; w < WARPS; ++w) tile_count += s_hist[w * kRadix + tid];
             st_relaxed_gpu_u64(desc + static_cast<uint64_t>(tile) * kRadix + tid,
                                desc_pack(epoch, kFlagReduction, tile_count));
         }
@@ -279,7 +297,7 @@ digit_binning_tile_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
         if (tid < kRadix) {
             uint32_t run = tile_excl;
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) { s_hist[w * kRadix + tid] = run; run += wcount[w]; }
+            for (int w = 0; w < WARPS; ++w) { const uint32_t c = s_hist[w * kRadix + tid]; s_hist[w * kRadix + tid] = run; run += c; }
         }
     }
     __syncthreads();
@@ -340,6 +358,201 @@ digit_binning_tile_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     }
 }
 
+// =====================================================================================================
+// DigitBinningPass, variant 1: persistent CTAs, partition tiles staged by TMA bulk copies (cp.async.bulk,
+// SASS UBLKCP) into a two-deep shared-memory ring.  While a CTA ranks and scatters tile p, the keys of its
+// next tile are already in flight, so neither the tile-ticket round trip nor the HBM load latency is on the
+// per-tile critical path.  Tickets are still handed out in increasing order and each CTA consumes its
+// tickets in order, so the lowest unfinished tile is always being processed by a resident CTA: the chained
+// scan cannot deadlock (same argument as the reference's dynamic partition index, OneSweep.cu:181-184).
+// =====================================================================================================
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy completing on an mbarrier (bytes and both addresses multiples of 16)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+template <typename KeyT, int K, int WARPS>
+struct PersistSmem {
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int T = THREADS * K;
+    alignas(128) KeyT stage[2][T];       // TMA destination; after ranking, the digit-sorted tile of the same slot
+    uint32_t hist[WARPS * kRadix];       // warp-private digit histograms
+    unsigned long long keyptr[kRadix];   // per digit: byte address of out[global_base - tile_base]
+    alignas(8) uint64_t bar[2];          // "stage filled" mbarriers
+    uint32_t tile[2];                    // ticket held in each stage
+    uint32_t wtot[kRadix / 32];
+};
+
+template <typename KeyT, int K, int WARPS, int RANK_MODE>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+digit_binning_persistent_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, uint64_t n, uint32_t shift,
+                                const unsigned long long* __restrict__ gbase, uint64_t* desc, uint32_t* ticket,
+                                uint32_t epoch, uint32_t num_tiles)
+{
+    using S = PersistSmem<KeyT, K, WARPS>;
+    constexpr int THREADS = S::THREADS;
+    constexpr int T = S::T;
+    constexpr uint32_t TILE_BYTES = T * sizeof(KeyT);
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    S& sm = *reinterpret_cast<S*>(s_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    uint32_t* wh = sm.hist + warp * kRadix;
+    const uint32_t warp_off = warp * (32 * K) + lane;
+
+    // a stage is filled by TMA only for full tiles; the (single) ragged last tile is read with guarded loads
+    auto fetch = [&](int slot) {  // thread 0 only
+        const uint32_t t = atomicAdd(ticket, 1u);
+        sm.tile[slot] = t;
+        if (t < num_tiles && static_cast<uint64_t>(t + 1) * T <= n) {
+            mbar_expect_tx(&sm.bar[slot], TILE_BYTES);
+            tma_load_1d(sm.stage[slot], in + static_cast<uint64_t>(t) * T, TILE_BYTES, &sm.bar[slot]);
+        }
+    };
+
+    for (int i = tid; i < WARPS * kRadix; i += THREADS) sm.hist[i] = 0;
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        fence_mbar_init();
+        fetch(0);
+        fetch(1);
+    }
+    __syncthreads();
+
+    for (uint32_t it = 0;; ++it) {
+        const int slot = it & 1;
+        const uint32_t tile = sm.tile[slot];
+        if (tile >= num_tiles) break;  // tickets only grow: nothing left for this CTA
+        const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
+        const bool full = tile_base + T <= n;
+        const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
+        KeyT* s_keys = sm.stage[slot];
+
+        // ---- keys: shared (TMA-filled) -> registers, warp-striped so every LDS row is conflict-free ------
+        KeyT key[K];
+        if (full) {
+            mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
+#pragma unroll
+            for (int i = 0; i < K; ++i) key[i] = s_keys[warp_off + i * 32];
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t idx = warp_off + i * 32;
+                key[i] = idx < valid ? in[tile_base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));
+            }
+        }
+
+        // ---- rank -------------------------------------------------------------------------------------
+        uint32_t off[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) off[i] = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
+        __syncthreads();  // (A) histograms complete; every key of the stage is in registers
+
+        // ---- per digit: prefix over warps, tile reduction, publish, scan over digits --------------------
+        uint32_t tile_count = 0, tile_excl = 0;
+        {
+            if (tid < kRadix) {
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
+                st_relaxed_gpu_u64(desc + static_cast<uint64_t>(tile) * kRadix + tid,
+                                   desc_pack(epoch, kFlagReduction, tile_count));
+            }
+            tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);  // (B) inside
+            if (tid < kRadix) {
+                uint32_t run = tile_excl;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
+            }
+        }
+        __syncthreads();  // (C)
+
+        // ---- transpose: the stage now receives the digit-sorted tile --------------------------------------
+#pragma unroll
+        for (int i = 0; i < K; ++i) s_keys[off[i] + wh[digit_of(key[i], shift)]] = key[i];
+
+        // ---- chained scan with decoupled lookback --------------------------------------------------------
+        if (tid < kRadix) {
+            const unsigned long long excl = lookback_and_publish(desc, tile, tid, tile_count, epoch, gbase);
+            sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + (excl - tile_excl) * sizeof(KeyT);
+        }
+        __syncthreads();  // (D) sorted tile + digit pointers ready; histograms dead
+
+        // ---- scatter -------------------------------------------------------------------------------------
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            if (idx < valid) {
+                const KeyT k = s_keys[idx];
+                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[digit_of(k, shift)]) + idx, k);
+            }
+        }
+        for (int i = tid; i < WARPS * kRadix; i += THREADS) sm.hist[i] = 0;
+        __syncthreads();  // (E) stage drained, histograms cleared
+        if (tid == 0) {
+            fence_proxy_async_smem();  // generic-proxy accesses of the stage happen-before the next TMA write
+            fetch(slot);
+        }
+        // the other stage's ticket was written at least one iteration (and one barrier) ago
+    }
+}
+
+template <typename KeyT> struct PersistGeom;
+template <> struct PersistGeom<uint32_t> { static constexpr int K = 16, WARPS = 16; };
+template <> struct PersistGeom<uint64_t> { static constexpr int K = 8,  WARPS = 16; };
+
+template <typename KeyT, int RANK_MODE>
+static cudaError_t launch_persistent_variant(const void* in, void* out, uint64_t n, uint32_t shift,
+                                             const unsigned long long* gbase, uint64_t* desc, uint32_t* ticket,
+                                             uint32_t epoch, int sm_count, cudaStream_t stream)
+{
+    using G = PersistGeom<KeyT>;
+    using S = PersistSmem<KeyT, G::K, G::WARPS>;
+    const uint64_t tiles = (n + S::T - 1) / S::T;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * 2;
+    const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+    auto kern = digit_binning_persistent_kernel<KeyT, G::K, G::WARPS, RANK_MODE>;
+    kern<<<grid, S::THREADS, sizeof(S), stream>>>(static_cast<const KeyT*>(in), static_cast<KeyT*>(out), n, shift, gbase,
+                                                   desc, ticket, epoch, static_cast<uint32_t>(tiles));
+    return cudaGetLastError();
+}
+
+template <typename KeyT, int RANK_MODE>
+static cudaError_t set_persistent_attr()
+{
+    using G = PersistGeom<KeyT>;
+    using S = PersistSmem<KeyT, G::K, G::WARPS>;
+    return cudaFuncSetAttribute(digit_binning_persistent_kernel<KeyT, G::K, G::WARPS, RANK_MODE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+}
+
 // ---- variant-0 geometry ------------------------------------------------------------------------------
 template <typename KeyT, bool PAIRS> struct TileGeom;
 template <> struct TileGeom<uint32_t, false> { static constexpr int K = 16, WARPS = 16; };
@@ -389,12 +602,20 @@ static cudaError_t set_tile_attr()
 cudaError_t configure_kernels()
 {
     cudaError_t e;
+    if ((e = cudaFuncSetAttribute(global_histogram_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(hist_smem_bytes<uint32_t>()))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(global_histogram_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(hist_smem_bytes<uint64_t>()))) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint32_t, false, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint32_t, false, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint32_t, true, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint32_t, true, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint64_t, false, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint64_t, false, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_persistent_attr<uint32_t, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_persistent_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_persistent_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_persistent_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -404,6 +625,14 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
+    if (cfg.variant == kVariantPersistent && !pairs) {
+        if (key_bytes == 4)
+            return ballot ? launch_persistent_variant<uint32_t, kRankBallot>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream)
+                          : launch_persistent_variant<uint32_t, kRankAtomic>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream);
+        if (key_bytes == 8)
+            return ballot ? launch_persistent_variant<uint64_t, kRankBallot>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream)
+                          : launch_persistent_variant<uint64_t, kRankAtomic>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream);
+    }
 #define OSB_DISPATCH(KEYT, PAIRS)                                                                                   \
     (ballot ? launch_tile_variant<KEYT, PAIRS, kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, desc,  \
                                                            ticket, epoch, stream)                                   \

@@ -9,6 +9,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+DEFAULT_VARIANT = 0
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_onesweep_golden.json")
 
 
@@ -50,9 +52,11 @@ def test_init_random_matches_oracle(g, oracle):
         assert np.array_equal(host_u32(t), oracle.init_random_u32(n, andc, seed))
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_keys_u32_edge_sizes(sorter, oracle, mode):
+def test_keys_u32_edge_sizes(sorter, oracle, mode, variant):
     sorter.set_option("rank_mode", mode)
+    sorter.set_option("variant", variant)
     T = tile_keys(sorter)
     sizes = [0, 1, 2, 3, 31, 32, 33, 255, 256, 257, 1000, T - 1, T, T + 1, 2 * T - 1, 2 * T, 2 * T + 1, 3 * T + 17, 100003]
     try:
@@ -61,33 +65,44 @@ def test_keys_u32_edge_sizes(sorter, oracle, mode):
             t = torch.empty(max(n, 4), dtype=torch.int32, device="cuda")
             t[:n] = dev_u32(k)
             sorter.sort_keys(t, n)
-            assert np.array_equal(host_u32(t[:n]), oracle.sort_keys(k)), f"n={n} mode={mode}"
+            assert np.array_equal(host_u32(t[:n]), oracle.sort_keys(k)), f"n={n} mode={mode} variant={variant}"
     finally:
         sorter.set_option("rank_mode", 0)
+        sorter.set_option("variant", DEFAULT_VARIANT)
 
 
-def test_reference_size_sweep(sorter, oracle):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_reference_size_sweep(sorter, oracle, variant):
     """The reference's TestAllKeysOnly sweep shape (OneSweepDispatcher.cuh:98-113): sizes across one..two of ITS
     tiles (7680..15360) and across one..two of OUR tiles, seed = n, checked bit-exactly (the reference only
     checks sortedness)."""
     T = tile_keys(sorter)
     sizes = list(range(7680, 15361, 193)) + list(range(T, 2 * T + 1, 331))
     buf = torch.empty(max(sizes), dtype=torch.int32, device="cuda")
-    for n in sizes:
-        k = oracle.init_random_u32(n, 0, n)
-        buf[:n] = dev_u32(k)
-        sorter.sort_keys(buf, n)
-        assert np.array_equal(host_u32(buf[:n]), oracle.sort_keys(k)), f"n={n}"
+    sorter.set_option("variant", variant)
+    try:
+        for n in sizes:
+            k = oracle.init_random_u32(n, 0, n)
+            buf[:n] = dev_u32(k)
+            sorter.sort_keys(buf, n)
+            assert np.array_equal(host_u32(buf[:n]), oracle.sort_keys(k)), f"n={n}"
+    finally:
+        sorter.set_option("variant", DEFAULT_VARIANT)
 
 
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("andc", [0, 1, 2, 3, 4])
-def test_entropy_presets_2pow20(sorter, oracle, andc):
-    n = 1 << 20
-    k = oracle.init_random_u32(n, andc, 10)
-    t = dev_u32(k)
-    sorter.sort_keys(t)
-    assert np.array_equal(host_u32(t), oracle.sort_keys(k))
-    assert sorter.validate(t) == 0
+def test_entropy_presets_2pow22(sorter, oracle, andc, variant):
+    n = 1 << 22
+    sorter.set_option("variant", variant)
+    try:
+        k = oracle.init_random_u32(n, andc, 10)
+        t = dev_u32(k)
+        sorter.sort_keys(t)
+        assert np.array_equal(host_u32(t), oracle.sort_keys(k))
+        assert sorter.validate(t) == 0
+    finally:
+        sorter.set_option("variant", DEFAULT_VARIANT)
 
 
 def test_adversarial_distributions(sorter, oracle):
@@ -125,8 +140,10 @@ def test_pairs_are_stable_payload_is_index(sorter, oracle, mode):
         sorter.set_option("rank_mode", 0)
 
 
-def test_keys_u64(g, oracle):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_keys_u64(g, oracle, variant):
     s = g.OneSweepSorter(1 << 21, 8, 0)
+    s.set_option("variant", variant)
     T = s.info("tile_keys")
     for n in [0, 1, 2, T - 1, T + 1, 5 * T + 11, 1 << 20]:
         k = oracle.init_random_u64(n, 0, 10 + n) if n else np.empty(0, np.uint64)

@@ -37,19 +37,23 @@ def main():
         g.init_random(src, 0, 10)
         work = torch.empty_like(src)
         s = g.OneSweepSorter(n, 4, 0)
-        for mode in (0, 1):
-            s.set_option("rank_mode", mode)
-            med, best = time_ms(lambda: s.sort_keys(work), prep=lambda: work.copy_(src))
-            print(f"n=2^{e} keys u32 rank_mode={mode}: median {med:.3f} ms best {best:.3f} ms -> {n/med/1e6:.1f} Gkeys/s, "
-                  f"{32*n/med/1e6/PEAK*100:.1f}% of {PEAK} GB/s (32 B/key)", flush=True)
-        s.set_option("rank_mode", 0)
-        # kernel split
+        VARIANTS = [int(x) for x in os.environ.get("OSB_VARIANTS", "0,1").split(",")]
+        MODES = [int(x) for x in os.environ.get("OSB_MODES", "0").split(",")]
         hist_ms, _ = time_ms(lambda: s.global_histogram(src))
+        print(f"n=2^{e} global_histogram(+memset) {hist_ms:.3f} ms ({4*n/hist_ms/1e6:.0f} GB/s read)", flush=True)
         dst = torch.empty_like(src)
-        pass_ms, _ = time_ms(lambda: s.digit_binning_pass(src, dst, 8))
-        print(f"   global_histogram(+memset) {hist_ms:.3f} ms ({4*n/hist_ms/1e6:.0f} GB/s read); "
-              f"hist+scan+one pass {pass_ms:.3f} ms => pass ~{pass_ms-hist_ms:.3f} ms "
-              f"({8*n/(pass_ms-hist_ms)/1e6:.0f} GB/s r+w)", flush=True)
+        for variant in VARIANTS:
+            s.set_option("variant", variant)
+            for mode in MODES:
+                s.set_option("rank_mode", mode)
+                med, best = time_ms(lambda: s.sort_keys(work), prep=lambda: work.copy_(src))
+                print(f"n=2^{e} keys u32 variant={variant} rank_mode={mode}: median {med:.3f} ms best {best:.3f} ms -> {n/med/1e6:.1f} Gkeys/s, "
+                      f"{32*n/med/1e6/PEAK*100:.1f}% of {PEAK} GB/s (32 B/key)", flush=True)
+            s.set_option("rank_mode", 0)
+            for shift in (0, 24):
+                pass_ms, _ = time_ms(lambda: s.digit_binning_pass(src, dst, shift))
+                print(f"   variant={variant} shift={shift}: hist+scan+one pass {pass_ms:.3f} ms => pass ~{pass_ms-hist_ms:.3f} ms "
+                      f"({8*n/(pass_ms-hist_ms)/1e6:.0f} GB/s r+w)", flush=True)
         assert s.validate(work) == 0
         s.close()
         del dst
