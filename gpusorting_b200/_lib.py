@@ -32,6 +32,7 @@ SIGNATURES = {
     "osb200_init_random_u32": (c_int, [c_vp, c_vp, c_u64, c_u32, c_u32, c_int, c_vp]),
     "osb200_set_option": (c_int, [c_vp, ctypes.c_char_p, c_i64]),
     "osb200_get_info": (c_i64, [c_vp, ctypes.c_char_p]),
+    "osb200_get_profile": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float), c_int]),
     "osb200_sharded_unique_id": (c_int, [c_vp]),
     "osb200_sharded_create": (c_int, [ctypes.POINTER(c_vp), c_vp, c_int, c_int, c_u64, c_int]),
     "osb200_sharded_destroy": (c_int, [c_vp]),

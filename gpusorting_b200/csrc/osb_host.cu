@@ -15,6 +15,7 @@
 #include "../../include/onesweep_b200.h"
 #include "osb_kernels.cuh"
 #include "osb_common.cuh"
+#include "osb_internal.h"
 
 namespace {
 
@@ -53,9 +54,15 @@ struct osb200_sorter {
     void* alt_keys = nullptr;
     uint32_t* alt_vals = nullptr;
     unsigned char* control = nullptr;  // ControlLayout
-    uint64_t* desc = nullptr;          // [tiles][256]
+    uint64_t* desc = nullptr;          // [tiles][256] 64-bit descriptors (epoch-stamped, never cleared)
+    uint16_t* agg16 = nullptr;         // [places][tiles][256] compact reductions (zeroed once per sort)
     uint64_t desc_tiles = 0;
     uint32_t epoch = 0;
+
+    // optional per-kernel timing of the last sort (osb200_set_option "profile"): events on the launching stream
+    bool profile = false;
+    cudaEvent_t ev[kMaxPlaces + 3] = {};
+    int ev_count = 0;
 
     // lazily created staging for the host-buffer entry points
     void* stage_keys = nullptr;
@@ -80,9 +87,12 @@ uint32_t smallest_tile(int key_bytes, bool pairs)
     // descriptors are sized for the smallest tile any variant may use
     osb::BinningConfig c;
     uint32_t t = osb::binning_tile_keys(key_bytes, pairs, c);
-    c.variant = osb::kVariantPersistent;
-    const uint32_t t2 = osb::binning_tile_keys(key_bytes, pairs, c);
-    return t2 < t ? t2 : t;
+    for (int v = 1; v < osb::kNumVariants; ++v) {
+        c.variant = v;
+        const uint32_t t2 = osb::binning_tile_keys(key_bytes, pairs, c);
+        if (t2 < t) t = t2;
+    }
+    return t;
 }
 
 // advance the epoch; on wrap-around clear the descriptors once (every ~16M passes)
@@ -108,8 +118,21 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
     const int places = s->key_bytes;
 
     OSB_TRY(cudaMemsetAsync(s->control, 0, ControlLayout::zeroed_bytes, stream));
+    const bool wide = s->cfg.variant == osb::kVariantWide && !d_vals;
+    const uint64_t agg_stride = tiles_for(n, osb::binning_tile_keys(s->key_bytes, d_vals != nullptr, s->cfg)) * osb::kRadix;
+    if (wide) OSB_TRY(cudaMemsetAsync(s->agg16, 0, agg_stride * places * sizeof(uint16_t), stream));
+    int ne = 0;
+    auto mark = [&]() -> cudaError_t {
+        if (!s->profile) return cudaSuccess;
+        if (!s->ev[ne]) { cudaError_t e = cudaEventCreate(&s->ev[ne]); if (e != cudaSuccess) return e; }
+        return cudaEventRecord(s->ev[ne++], stream);
+    };
+    s->ev_count = 0;
+    OSB_TRY(mark());
     OSB_TRY(osb::launch_global_histogram(d_keys, n, s->key_bytes, s->ghist(), s->sm_count, stream));
+    OSB_TRY(mark());
     OSB_TRY(osb::launch_scan(s->ghist(), s->gbase(), places, stream));
+    OSB_TRY(mark());
 
     void* src = d_keys;
     void* dst = s->alt_keys;
@@ -120,10 +143,13 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
         int st = next_epoch(s, stream, &epoch);
         if (st != OSB200_OK) return st;
         OSB_TRY(osb::launch_digit_binning(src, dst, sv, dv, n, s->key_bytes, static_cast<uint32_t>(p) * 8u,
-                                          s->gbase() + p * osb::kRadix, s->desc, s->tickets() + p, epoch, s->cfg, stream));
+                                          s->gbase() + p * osb::kRadix, s->desc, s->agg16 + p * agg_stride,
+                                          s->tickets() + p, epoch, s->cfg, stream));
+        OSB_TRY(mark());
         void* t = src; src = dst; dst = t;
         uint32_t* tv = sv; sv = dv; dv = tv;
     }
+    s->ev_count = ne;
     return OSB200_OK;  // even number of passes: result is back in d_keys / d_vals
 }
 
@@ -159,6 +185,39 @@ int sort_host_impl(osb200_sorter* s, void* h_keys, uint32_t* h_vals, uint64_t n)
 
 }  // namespace
 
+// ---- internal interfaces used by the sharded path (osb_internal.h) -----------------------------------------
+int osb_internal_digit_histogram(osb200_handle h, const void* d_in, uint64_t n, uint32_t shift,
+                                 unsigned long long* d_hist256, cudaStream_t stream)
+{
+    OSB_TRY(cudaMemsetAsync(d_hist256, 0, osb::kRadix * sizeof(unsigned long long), stream));
+    if (n) OSB_TRY(osb::launch_digit_histogram(d_in, n, h->key_bytes, shift, d_hist256, h->sm_count, stream));
+    return OSB200_OK;
+}
+
+int osb_internal_binning_pass(osb200_handle h, const void* d_in, void* d_out, uint64_t n, uint32_t shift,
+                              const unsigned long long* d_hist256, const unsigned long long* out_base,
+                              cudaStream_t stream)
+{
+    if (n == 0) return OSB200_OK;
+    if (n > h->max_n) return OSB200_ERR_SIZE;
+    const unsigned long long* base = out_base;
+    OSB_TRY(cudaMemsetAsync(h->tickets(), 0, ControlLayout::ticket_bytes, stream));
+    if (!base) {
+        OSB_TRY(osb::launch_scan(d_hist256, h->gbase(), 1, stream));
+        base = h->gbase();
+    }
+    if (h->cfg.variant == osb::kVariantWide) {
+        const uint64_t tiles = tiles_for(n, osb::binning_tile_keys(h->key_bytes, false, h->cfg));
+        OSB_TRY(cudaMemsetAsync(h->agg16, 0, tiles * osb::kRadix * sizeof(uint16_t), stream));
+    }
+    uint32_t epoch = 0;
+    int st = next_epoch(h, stream, &epoch);
+    if (st != OSB200_OK) return st;
+    OSB_TRY(osb::launch_digit_binning(d_in, d_out, nullptr, nullptr, n, h->key_bytes, shift, base, h->desc, h->agg16,
+                                      h->tickets(), epoch, h->cfg, stream));
+    return OSB200_OK;
+}
+
 extern "C" {
 
 int osb200_version(void) { return kVersion; }
@@ -183,7 +242,8 @@ uint64_t osb200_workspace_bytes(uint64_t max_n, int key_bytes, int value_bytes)
 {
     if ((key_bytes != 4 && key_bytes != 8) || (value_bytes != 0 && value_bytes != 4)) return 0;
     const uint64_t tiles = tiles_for(max_n ? max_n : 1, smallest_tile(key_bytes, value_bytes != 0));
-    return max_n * key_bytes + max_n * value_bytes + tiles * osb::kRadix * sizeof(uint64_t) + ControlLayout::total;
+    return max_n * key_bytes + max_n * value_bytes + tiles * osb::kRadix * (sizeof(uint64_t) + sizeof(uint16_t) * key_bytes) +
+           ControlLayout::total;
 }
 
 int osb200_create(osb200_handle* out, uint64_t max_n, int key_bytes, int value_bytes)
@@ -217,6 +277,7 @@ int osb200_create(osb200_handle* out, uint64_t max_n, int key_bytes, int value_b
     if (ok && value_bytes) ok = cudaMalloc(&s->alt_vals, max_n * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&s->control, ControlLayout::total) == cudaSuccess;
     ok = ok && cudaMalloc(&s->desc, s->desc_tiles * osb::kRadix * sizeof(uint64_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->agg16, s->desc_tiles * osb::kRadix * sizeof(uint16_t) * key_bytes) == cudaSuccess;
     if (!ok) { cudaGetLastError(); osb200_destroy(s); return OSB200_ERR_ALLOC; }
     e = cudaMemset(s->desc, 0, s->desc_tiles * osb::kRadix * sizeof(uint64_t));  // epoch 0 == never valid
     if (e == cudaSuccess) e = cudaMemset(s->control, 0, ControlLayout::total);
@@ -239,9 +300,11 @@ int osb200_destroy(osb200_handle h)
     cudaFree(h->alt_vals);
     cudaFree(h->control);
     cudaFree(h->desc);
+    cudaFree(h->agg16);
     cudaFree(h->stage_keys);
     cudaFree(h->stage_vals);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     delete h;
     return OSB200_OK;
 }
@@ -324,8 +387,11 @@ int osb200_digit_binning_pass(osb200_handle h, const void* d_in, void* d_out, co
     uint32_t epoch = 0;
     int st = next_epoch(h, q, &epoch);
     if (st != OSB200_OK) return st;
+    if (h->cfg.variant == osb::kVariantWide && !d_in_values)
+        OSB_TRY(cudaMemsetAsync(h->agg16, 0, h->desc_tiles * osb::kRadix * sizeof(uint16_t), q));
     OSB_TRY(osb::launch_digit_binning(d_in, d_out, d_in_values, d_out_values, n, h->key_bytes, radix_shift,
-                                      h->gbase() + place * osb::kRadix, h->desc, h->tickets() + place, epoch, h->cfg, q));
+                                      h->gbase() + place * osb::kRadix, h->desc, h->agg16, h->tickets() + place, epoch,
+                                      h->cfg, q));
     return OSB200_OK;
 }
 
@@ -364,12 +430,23 @@ int osb200_set_option(osb200_handle h, const char* key, int64_t value)
         h->cfg.rank_mode = static_cast<int>(value);
         return OSB200_OK;
     }
+    if (!std::strcmp(key, "profile")) { h->profile = value != 0; return OSB200_OK; }
     if (!std::strcmp(key, "variant")) {
-        if (value != osb::kVariantTilePerCta && value != osb::kVariantPersistent) return OSB200_ERR_INVALID_ARG;
+        if (value < 0 || value >= osb::kNumVariants) return OSB200_ERR_INVALID_ARG;
         h->cfg.variant = static_cast<int>(value);
         return OSB200_OK;
     }
     return OSB200_ERR_INVALID_ARG;
+}
+
+int osb200_get_profile(osb200_handle h, float* out_ms, int capacity)
+{
+    if (check_handle(h) != OSB200_OK || !out_ms) return OSB200_ERR_INVALID_ARG;
+    if (h->ev_count < 2) return 0;
+    OSB_TRY(cudaEventSynchronize(h->ev[h->ev_count - 1]));
+    int k = 0;
+    for (int i = 0; i + 1 < h->ev_count && k < capacity; ++i, ++k) OSB_TRY(cudaEventElapsedTime(&out_ms[k], h->ev[i], h->ev[i + 1]));
+    return k;
 }
 
 int64_t osb200_get_info(osb200_handle h, const char* key)
@@ -377,7 +454,7 @@ int64_t osb200_get_info(osb200_handle h, const char* key)
     if (check_handle(h) != OSB200_OK || !key) return OSB200_ERR_INVALID_ARG;
     if (!std::strcmp(key, "tile_keys")) return osb::binning_tile_keys(h->key_bytes, h->value_bytes != 0, h->cfg);
     if (!std::strcmp(key, "launches_per_sort")) return 2 + h->key_bytes;  // histogram + scan + one pass per place
-    if (!std::strcmp(key, "memsets_per_sort")) return 1;
+    if (!std::strcmp(key, "memsets_per_sort")) return (h->cfg.variant == osb::kVariantWide && !h->value_bytes) ? 2 : 1;
     if (!std::strcmp(key, "sm_count")) return h->sm_count;
     if (!std::strcmp(key, "rank_mode")) return h->cfg.rank_mode;
     if (!std::strcmp(key, "variant")) return h->cfg.variant;

@@ -123,6 +123,49 @@ cudaError_t launch_global_histogram(const void* keys, uint64_t n, int key_bytes,
     return cudaGetLastError();
 }
 
+// Single digit place (the sharded path's most-significant-digit histogram): one atomic per key, same
+// bank-private column layout, 32 KB of shared memory.
+template <typename KeyT>
+__global__ void __launch_bounds__(kHistThreads, 1)
+digit_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, uint32_t shift, unsigned long long* __restrict__ hist256)
+{
+    __shared__ uint32_t s_hist[kRadix * 32];
+    for (int i = threadIdx.x; i < kRadix * 32; i += kHistThreads) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t* s_col = s_hist + (threadIdx.x & 31);
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kHistThreads;
+    uint64_t i = static_cast<uint64_t>(blockIdx.x) * kHistThreads + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        const KeyT a = __ldcs(keys + i), b = __ldcs(keys + i + stride), c = __ldcs(keys + i + 2 * stride),
+                   d = __ldcs(keys + i + 3 * stride);
+        atomicAdd(&s_col[digit_of(a, shift) * 32], 1u);
+        atomicAdd(&s_col[digit_of(b, shift) * 32], 1u);
+        atomicAdd(&s_col[digit_of(c, shift) * 32], 1u);
+        atomicAdd(&s_col[digit_of(d, shift) * 32], 1u);
+    }
+    for (; i < n; i += stride) atomicAdd(&s_col[digit_of(__ldcs(keys + i), shift) * 32], 1u);
+    __syncthreads();
+    for (int bin = threadIdx.x; bin < kRadix; bin += kHistThreads) {
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) sum += s_hist[bin * 32 + ((c + threadIdx.x) & 31)];
+        if (sum) atomicAdd(&hist256[bin], static_cast<unsigned long long>(sum));
+    }
+}
+
+cudaError_t launch_digit_histogram(const void* keys, uint64_t n, int key_bytes, uint32_t shift,
+                                   unsigned long long* hist256, int sm_count, cudaStream_t stream)
+{
+    uint64_t want = (n + kHistThreads * 4 - 1) / (kHistThreads * 4);
+    if (want < 1) want = 1;
+    const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 2 ? want : sm_count * 2);
+    if (key_bytes == 4)
+        digit_histogram_kernel<uint32_t><<<grid, kHistThreads, 0, stream>>>(static_cast<const uint32_t*>(keys), n, shift, hist256);
+    else
+        digit_histogram_kernel<uint64_t><<<grid, kHistThreads, 0, stream>>>(static_cast<const uint64_t*>(keys), n, shift, hist256);
+    return cudaGetLastError();
+}
+
 // =====================================================================================================
 // Scan: exclusive prefix over the 256 bins of each digit place
 // =====================================================================================================
@@ -553,6 +596,211 @@ static cudaError_t set_persistent_attr()
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
 }
 
+// =====================================================================================================
+// DigitBinningPass, variant 2 ("wide tile"): 16,384-key partition tiles, two CTAs per SM.
+//
+// Why the tile is this large.  In a chained scan the number of predecessor tiles that have published only their
+// reduction when a tile starts looking back is (tiles entering per second) x (latency from publishing a reduction
+// to publishing the inclusive prefix).  ncu on variant 0 (8,192-key tiles) shows exactly that: 11 lookback steps
+// per tile at 31 tiles/us and ~0.35 us per L2 round trip, i.e. the lookback was the critical path
+// (profiles/r01_ncu_v1_tile_per_cta.md).  At the B200 target rate the window would be ~33 tiles.  Doubling the tile
+// halves the window and halves the per-key cost of each step; the remaining window (~16) is covered in ONE round
+// trip by issuing all of its loads at once.  To keep that affordable the reductions live in a compact array of
+// 16-bit words (flag:1 | count:15 -- a tile holds at most 16,384 keys), 512 B per tile instead of 2 KB; only the
+// inclusive prefixes use the 64-bit epoch-stamped descriptors.
+//
+// Ranking is two shared-memory atomics per key on warp-private histograms: a non-returning count, then -- after
+// the per-digit bases of the tile have been scanned into the same counters -- a returning atomicAdd whose result
+// IS the key's slot in the digit-sorted tile (lane-ordered, see top of file).  No per-key offsets are kept in
+// registers, so 32 keys per thread fit in a 64-register budget (2 x 512 threads per SM).
+// =====================================================================================================
+constexpr uint32_t kAggReady = 0x8000u;   // agg16 word: bit 15 = reduction published, bits 0..14 = count
+
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_u16(const uint16_t* p)
+{
+    uint16_t v;
+    asm volatile("ld.relaxed.gpu.global.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_u16(uint16_t* p, uint32_t v)
+{
+    asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
+}
+
+// Decoupled lookback over the compact reductions.  Examines up to LOOK predecessors per round trip, with an
+// inclusive-prefix probe every STEP tiles.  Returns the exclusive global prefix of (tile, digit d).
+template <int LOOK, int STEP>
+__device__ __forceinline__ unsigned long long
+lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d, uint32_t epoch,
+              const unsigned long long* __restrict__ gbase)
+{
+    static_assert(LOOK % STEP == 0, "probe spacing must divide the window");
+    unsigned long long sum = 0;                       // reductions of tiles (cur, tile-1] already added
+    int64_t cur = static_cast<int64_t>(tile) - 1;     // nearest predecessor not yet accounted for
+    while (true) {
+        if (cur < 0) return sum + gbase[d];
+        uint32_t a[LOOK];
+        uint64_t c[LOOK / STEP];
+#pragma unroll
+        for (int i = 0; i < LOOK; ++i) {
+            const int64_t t = cur - i;
+            a[i] = t >= 0 ? ld_relaxed_gpu_u16(agg16 + t * kRadix + d) : kAggReady;
+        }
+#pragma unroll
+        for (int j = 0; j < LOOK / STEP; ++j) {
+            const int64_t t = cur - (j * STEP + STEP - 1);
+            c[j] = t >= 0 ? ld_relaxed_gpu_u64(incl64 + t * kRadix + d) : 0ull;
+        }
+        unsigned long long run = sum;
+        int64_t next = cur - LOOK;  // where to continue if the whole window was reductions only
+        bool stalled = false;
+#pragma unroll
+        for (int i = 0; i < LOOK; ++i) {
+            const int64_t t = cur - i;
+            if (t < 0) return run + gbase[d];
+            if ((i % STEP) == STEP - 1) {
+                const uint64_t v = c[i / STEP];
+                if (desc_epoch(v) == epoch && (v & kFlagMask) == kFlagInclusive) return run + desc_value(v);
+            }
+            if (!(a[i] & kAggReady)) { next = t; stalled = true; break; }
+            run += a[i] & 0x7fffu;
+        }
+        sum = run;
+        cur = next;
+        if (stalled) __nanosleep(40);
+    }
+}
+
+template <typename KeyT, int K, int WARPS>
+struct WideSmem {
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int T = THREADS * K;
+    alignas(16) KeyT sorted[T];          // digit-sorted tile
+    uint32_t hist[WARPS * kRadix];       // warp-private digit counters (counts, then running slots)
+    unsigned long long off[kRadix];      // per digit: out index of tile slot 0 "as if" of this digit
+    uint32_t wtot[kRadix / 32];
+    uint32_t tile;
+};
+
+template <typename KeyT, int K, int WARPS, int RANK_MODE, int LOOK, int STEP>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, uint64_t n, uint32_t shift,
+                          const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
+                          uint32_t* ticket, uint32_t epoch)
+{
+    using S = WideSmem<KeyT, K, WARPS>;
+    constexpr int THREADS = S::THREADS;
+    constexpr int T = S::T;
+    static_assert(T <= 16384, "agg16 holds 15-bit counts");
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    S& sm = *reinterpret_cast<S*>(s_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    uint32_t* wh = sm.hist + warp * kRadix;
+
+    for (int i = tid; i < WARPS * kRadix; i += THREADS) sm.hist[i] = 0;
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
+    const bool full = tile_base + T <= n;
+    const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
+
+    // ---- load (warp-striped: every warp instruction reads one contiguous 128 B / 256 B row) ------------
+    KeyT key[K];
+    const uint32_t warp_off = warp * (32 * K) + lane;
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) key[i] = ld_stream(in + tile_base + warp_off + i * 32);
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const uint32_t idx = warp_off + i * 32;
+            key[i] = idx < valid ? in[tile_base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));  // pad: ranks last
+        }
+    }
+
+    // ---- phase 1: count digits per warp (order-free, non-returning atomics) ---------------------------
+#pragma unroll
+    for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift)], 1u);
+    __syncthreads();
+
+    // ---- per digit: tile reduction -> publish; scan over digits; per-warp slot bases --------------------
+    uint32_t tile_count = 0, tile_excl = 0;
+    if (tid < kRadix) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
+        st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+    }
+    tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
+    if (tid < kRadix) {
+        uint32_t run = tile_excl;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
+    }
+    __syncthreads();
+
+    // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -----------------
+#pragma unroll
+    for (int i = 0; i < K; ++i) sm.sorted[warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt)] = key[i];
+
+    // ---- chained scan with decoupled lookback ------------------------------------------------------------
+    if (tid < kRadix) {
+        const unsigned long long excl = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch, gbase);
+        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
+                           desc_pack(epoch, kFlagInclusive, excl + tile_count));
+        sm.off[tid] = excl - tile_excl;
+    }
+    __syncthreads();
+
+    // ---- scatter -----------------------------------------------------------------------------------------
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            const KeyT k = sm.sorted[idx];
+            st_stream(out + (sm.off[digit_of(k, shift)] + idx), k);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            if (idx < valid) {
+                const KeyT k = sm.sorted[idx];
+                st_stream(out + (sm.off[digit_of(k, shift)] + idx), k);
+            }
+        }
+    }
+}
+
+template <typename KeyT> struct WideGeom;
+template <> struct WideGeom<uint32_t> { static constexpr int K = 32, WARPS = 16; };
+template <> struct WideGeom<uint64_t> { static constexpr int K = 16, WARPS = 16; };
+constexpr int kWideLook = 16, kWideStep = 8;
+
+template <typename KeyT, int RANK_MODE>
+static cudaError_t launch_wide_variant(const void* in, void* out, uint64_t n, uint32_t shift, const unsigned long long* gbase,
+                                       uint16_t* agg16, uint64_t* incl64, uint32_t* ticket, uint32_t epoch, cudaStream_t stream)
+{
+    using G = WideGeom<KeyT>;
+    using S = WideSmem<KeyT, G::K, G::WARPS>;
+    const uint64_t tiles = (n + S::T - 1) / S::T;
+    auto kern = digit_binning_wide_kernel<KeyT, G::K, G::WARPS, RANK_MODE, kWideLook, kWideStep>;
+    kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
+        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), n, shift, gbase, agg16, incl64, ticket, epoch);
+    return cudaGetLastError();
+}
+
+template <typename KeyT, int RANK_MODE>
+static cudaError_t set_wide_attr()
+{
+    using G = WideGeom<KeyT>;
+    using S = WideSmem<KeyT, G::K, G::WARPS>;
+    return cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, G::K, G::WARPS, RANK_MODE, kWideLook, kWideStep>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+}
+
 // ---- variant-0 geometry ------------------------------------------------------------------------------
 template <typename KeyT, bool PAIRS> struct TileGeom;
 template <> struct TileGeom<uint32_t, false> { static constexpr int K = 16, WARPS = 16; };
@@ -584,7 +832,9 @@ static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t
 
 uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
 {
-    (void)cfg;
+    if (cfg.variant == kVariantWide && !pairs)
+        return key_bytes == 8 ? WideSmem<uint64_t, WideGeom<uint64_t>::K, WideGeom<uint64_t>::WARPS>::T
+                              : WideSmem<uint32_t, WideGeom<uint32_t>::K, WideGeom<uint32_t>::WARPS>::T;
     if (key_bytes == 8) return TileGeom<uint64_t, false>::WARPS * 32 * TileGeom<uint64_t, false>::K;
     if (pairs) return TileGeom<uint32_t, true>::WARPS * 32 * TileGeom<uint32_t, true>::K;
     return TileGeom<uint32_t, false>::WARPS * 32 * TileGeom<uint32_t, false>::K;
@@ -616,15 +866,28 @@ cudaError_t configure_kernels()
     if ((e = set_persistent_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_persistent_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_persistent_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
 cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
                                  int key_bytes, uint32_t shift, const unsigned long long* gbase_place, uint64_t* desc,
-                                 uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg, cudaStream_t stream)
+                                 uint16_t* agg16, uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg,
+                                 cudaStream_t stream)
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
+    if (cfg.variant == kVariantWide && !pairs) {
+        if (key_bytes == 4)
+            return ballot ? launch_wide_variant<uint32_t, kRankBallot>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, stream)
+                          : launch_wide_variant<uint32_t, kRankAtomic>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, stream);
+        if (key_bytes == 8)
+            return ballot ? launch_wide_variant<uint64_t, kRankBallot>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, stream)
+                          : launch_wide_variant<uint64_t, kRankAtomic>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, stream);
+    }
     if (cfg.variant == kVariantPersistent && !pairs) {
         if (key_bytes == 4)
             return ballot ? launch_persistent_variant<uint32_t, kRankBallot>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream)

@@ -9,7 +9,9 @@ namespace osb {
 enum BinningVariant : int {
     kVariantTilePerCta = 0,  // one CTA per partition tile, keys loaded straight into registers
     kVariantPersistent = 1,  // persistent CTAs, TMA (cp.async.bulk) double-buffered tile staging
+    kVariantWide = 2,        // 16,384-key tiles, two-phase atomic ranking, compact reductions + one-shot lookback
 };
+constexpr int kNumVariants = 3;
 enum RankMode : int {
     kRankAtomic = 0,  // one shared-memory atomicAdd per key (lane-ordered on sm_100, verified at create)
     kRankBallot = 1,  // 8 ballots per key (the reference's warp-level multisplit, OneSweep.cu:208-253)
@@ -32,16 +34,22 @@ cudaError_t configure_kernels();
 cudaError_t launch_global_histogram(const void* keys, uint64_t n, int key_bytes, unsigned long long* ghist,
                                     int sm_count, cudaStream_t stream);
 
+// Single-place histogram (used by the sharded path for the most significant digit): hist256[digit] += counts.
+cudaError_t launch_digit_histogram(const void* keys, uint64_t n, int key_bytes, uint32_t shift,
+                                   unsigned long long* hist256, int sm_count, cudaStream_t stream);
+
 // Scan (reference: OneSweep::Scan, Sort/OneSweep.cu:125-162): per place exclusive prefix of ghist -> gbase.
 cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream);
 
 // DigitBinningPass (reference: OneSweep::DigitBinningPassKeysOnly / Pairs, Sort/OneSweep.cu:164-600).
 //   gbase_place: [256] exclusive global digit bases for this digit place
 //   desc:        [tiles][256] 64-bit tile descriptors (never cleared; `epoch` distinguishes launches)
+//   agg16:       [tiles][256] 16-bit tile reductions (flag:1|count:15) used by kVariantWide; zeroed per sort
 //   ticket:      one zeroed u32 (dynamic tile id counter, reference `index[]`)
 cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
                                  int key_bytes, uint32_t shift, const unsigned long long* gbase_place, uint64_t* desc,
-                                 uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg, cudaStream_t stream);
+                                 uint16_t* agg16, uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg,
+                                 cudaStream_t stream);
 
 // Validate (reference: Validate, UtilityKernels.cuh:403-429): err_count += #(keys[i] > keys[i+1]).
 cudaError_t launch_validate(const void* keys, uint64_t n, int key_bytes, unsigned long long* err_count, int sm_count,

@@ -1,18 +1,332 @@
-// osb_sharded.cu -- multi-GPU sharded sort (MSD bucket exchange + local OneSweep).  Placeholder: filled in
-// after the single-GPU path is parity-green; until then every entry point reports OSB200_ERR_UNSUPPORTED.
+// osb_sharded.cu -- multi-GPU sharded sort: one MSD bucket-exchange pass over NVLink, then a local OneSweep.
+//
+// No reference equivalent (the reference is single-device); this is BASELINE.json's fifth config.
+// One process per GPU.  Every rank holds n_local unsorted keys; after the call rank r holds the r-th contiguous
+// slice of the global ascending order.
+//
+//   1. 256-bin histogram of the most significant digit of the local keys            (digit_histogram_kernel)
+//   2. all-gather of the R histograms                                                (ncclAllGather, 2 KB per rank)
+//   3. plan: contiguous bucket ranges -> ranks, balanced on the global counts        (osb200_sharded_plan, host)
+//   4. exchange pass, two implementations:
+//        fused  (default): the ordinary DigitBinningPass kernel scatters straight into the peers' receive buffers
+//                through CUDA-IPC-mapped NVLink addresses -- its per-digit output bases are "virtual element indices"
+//                that encode peer addresses, so ranking, chained scan and the NVLink stores are ONE kernel and the
+//                keys cross HBM once (read) + NVLink once (write);
+//        staged: DigitBinningPass into a local send buffer, then ncclSend/ncclRecv per peer (baseline).
+//   5. local OneSweep (osb200_sort_keys_u32) on the received keys.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <nccl.h>
+
 #include "../../include/onesweep_b200.h"
+#include "osb_internal.h"
+
+namespace {
+
+constexpr int kRadix = 256;
+constexpr int kMaxWorld = 64;
+
+inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? OSB200_OK : OSB200_ERR_CUDA - static_cast<int>(e); }
+#define OSB_TRY(expr)                                    \
+    do {                                                 \
+        cudaError_t e__ = (expr);                        \
+        if (e__ != cudaSuccess) return cuda_status(e__); \
+    } while (0)
+#define OSB_NCCL(expr)                                   \
+    do {                                                 \
+        ncclResult_t r__ = (expr);                       \
+        if (r__ != ncclSuccess) return OSB200_ERR_NCCL;  \
+    } while (0)
+
+}  // namespace
+
+struct osb200_sharded_sorter {
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    uint64_t max_n_local = 0, capacity = 0;  // capacity = receive-side keys (max_n_local + slack)
+    osb200_handle exch = nullptr;            // kernels/state for the exchange pass over the local input
+    osb200_handle local = nullptr;           // local OneSweep over the received keys
+    uint32_t* send_buf = nullptr;            // staged mode only
+    uint32_t* recv_buf = nullptr;
+    unsigned long long* d_hist = nullptr;      // [256] local MSD histogram
+    unsigned long long* d_hist_all = nullptr;  // [world][256]
+    unsigned long long* d_out_base = nullptr;  // [256] virtual element indices (fused mode)
+    unsigned long long* h_hist_all = nullptr;  // pinned
+    unsigned long long* h_out_base = nullptr;  // pinned
+    uint32_t* d_flag = nullptr;                // 1-element all-reduce used as a stream-ordered cross-GPU barrier
+    void* peer_recv[kMaxWorld] = {};           // IPC-mapped receive buffers of all ranks (own = recv_buf)
+    bool fused = true;
+    cudaEvent_t ev[4] = {};
+    float last_ms[4] = {0, 0, 0, 0};
+};
 
 extern "C" {
-int osb200_sharded_unique_id(void*) { return OSB200_ERR_UNSUPPORTED; }
-int osb200_sharded_create(osb200_sharded_handle* out, const void*, int, int, uint64_t, int)
+
+// Host-side plan shared by every rank (pure function of the all-gathered histograms; exported for CPU tests).
+//   hist_all   [world][256]  digit counts per source rank
+//   dest       [256]         owner rank of every bucket: contiguous, non-decreasing, balanced on global counts
+//   recv_count [world]       keys each rank ends up with
+//   recv_off   [world][256]  for THIS rank as a source (`rank`): element offset inside dest[d]'s receive buffer where
+//                            its keys of bucket d go.  Layout at a destination: bucket-major, source-rank-minor,
+//                            i.e. exactly the globally stable order of the MSD partition.
+OSB200_API int osb200_sharded_plan(const uint64_t* hist_all, int world, int rank, int32_t* dest, uint64_t* recv_count,
+                                   uint64_t* recv_off)
 {
-    if (out) *out = nullptr;
-    return OSB200_ERR_UNSUPPORTED;
+    if (!hist_all || !dest || !recv_count || !recv_off || world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+        return OSB200_ERR_INVALID_ARG;
+    uint64_t bucket[kRadix], total = 0;
+    for (int d = 0; d < kRadix; ++d) {
+        bucket[d] = 0;
+        for (int r = 0; r < world; ++r) bucket[d] += hist_all[r * kRadix + d];
+        total += bucket[d];
+    }
+    // greedy contiguous split: bucket d goes to the rank whose ideal range contains the bucket's midpoint
+    uint64_t before = 0;
+    int prev = 0;
+    for (int d = 0; d < kRadix; ++d) {
+        int q = prev;
+        if (total) {
+            const long double mid = static_cast<long double>(before) + static_cast<long double>(bucket[d]) / 2;
+            q = static_cast<int>(mid * world / static_cast<long double>(total));
+            if (q >= world) q = world - 1;
+            if (q < prev) q = prev;
+        }
+        dest[d] = q;
+        prev = q;
+        before += bucket[d];
+    }
+    for (int r = 0; r < world; ++r) recv_count[r] = 0;
+    uint64_t fill[kMaxWorld] = {};  // running fill of every destination, bucket-major
+    for (int d = 0; d < kRadix; ++d) {
+        const int q = dest[d];
+        uint64_t off = fill[q];
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) recv_off[d] = off;
+            off += hist_all[r * kRadix + d];
+        }
+        fill[q] = off;
+    }
+    for (int r = 0; r < world; ++r) recv_count[r] = fill[r];
+    return OSB200_OK;
 }
-int osb200_sharded_destroy(osb200_sharded_handle) { return OSB200_ERR_UNSUPPORTED; }
-int osb200_sharded_sort_keys_u32(osb200_sharded_handle, const uint32_t*, uint64_t, uint32_t**, uint64_t*, void*)
+
+int osb200_sharded_unique_id(void* out_128_bytes)
 {
-    return OSB200_ERR_UNSUPPORTED;
+    if (!out_128_bytes) return OSB200_ERR_INVALID_ARG;
+    static_assert(sizeof(ncclUniqueId) == 128, "unique id size");
+    ncclUniqueId id;
+    OSB_NCCL(ncclGetUniqueId(&id));
+    std::memcpy(out_128_bytes, &id, sizeof(id));
+    return OSB200_OK;
 }
-int osb200_sharded_last_timing(osb200_sharded_handle, float*) { return OSB200_ERR_UNSUPPORTED; }
+
+int osb200_sharded_destroy(osb200_sharded_handle h)
+{
+    if (!h) return OSB200_ERR_INVALID_ARG;
+    for (int r = 0; r < h->world; ++r)
+        if (r != h->rank && h->peer_recv[r]) cudaIpcCloseMemHandle(h->peer_recv[r]);
+    if (h->exch) osb200_destroy(h->exch);
+    if (h->local) osb200_destroy(h->local);
+    cudaFree(h->send_buf);
+    cudaFree(h->recv_buf);
+    cudaFree(h->d_hist);
+    cudaFree(h->d_hist_all);
+    cudaFree(h->d_out_base);
+    cudaFree(h->d_flag);
+    cudaFreeHost(h->h_hist_all);
+    cudaFreeHost(h->h_out_base);
+    for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->comm) ncclCommDestroy(h->comm);
+    delete h;
+    return OSB200_OK;
 }
+
+int osb200_sharded_create(osb200_sharded_handle* out, const void* unique_id_128_bytes, int rank, int world,
+                          uint64_t max_n_local, int slack_percent)
+{
+    if (!out) return OSB200_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (!unique_id_128_bytes || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || max_n_local == 0 ||
+        slack_percent < 0 || slack_percent > 400)
+        return OSB200_ERR_INVALID_ARG;
+    osb200_sharded_sorter* s = new (std::nothrow) osb200_sharded_sorter();
+    if (!s) return OSB200_ERR_ALLOC;
+    s->rank = rank;
+    s->world = world;
+    s->max_n_local = max_n_local;
+    s->capacity = max_n_local + max_n_local / 100 * slack_percent + 4096;
+
+    ncclUniqueId id;
+    std::memcpy(&id, unique_id_128_bytes, sizeof(id));
+    if (ncclCommInitRank(&s->comm, world, id, rank) != ncclSuccess) { osb200_sharded_destroy(s); return OSB200_ERR_NCCL; }
+
+    int st = osb200_create(&s->exch, max_n_local, 4, 0);
+    if (st == OSB200_OK) st = osb200_create(&s->local, s->capacity, 4, 0);
+    if (st != OSB200_OK) { osb200_sharded_destroy(s); return st; }
+    bool ok = cudaMalloc(&s->recv_buf, s->capacity * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_hist, kRadix * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_hist_all, static_cast<size_t>(world) * kRadix * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_out_base, kRadix * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_flag, 64) == cudaSuccess;
+    ok = ok && cudaMallocHost(&s->h_hist_all, static_cast<size_t>(world) * kRadix * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&s->h_out_base, kRadix * sizeof(unsigned long long)) == cudaSuccess;
+    for (auto& e : s->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); osb200_sharded_destroy(s); return OSB200_ERR_ALLOC; }
+    cudaMemset(s->d_flag, 0, 64);
+
+    // Map every peer's receive buffer (CUDA IPC over NVLink/NVSwitch; all ranks are processes on one node).
+    s->peer_recv[rank] = s->recv_buf;
+    s->fused = world > 1;
+    if (world > 1) {
+        cudaIpcMemHandle_t mine;
+        std::vector<cudaIpcMemHandle_t> all(world);
+        cudaIpcMemHandle_t* d_handles = nullptr;
+        bool ipc_ok = cudaIpcGetMemHandle(&mine, s->recv_buf) == cudaSuccess;
+        ipc_ok = ipc_ok && cudaMalloc(&d_handles, sizeof(cudaIpcMemHandle_t) * world) == cudaSuccess;
+        if (ipc_ok) {
+            cudaMemcpy(d_handles + rank, &mine, sizeof(mine), cudaMemcpyHostToDevice);
+            ncclResult_t r = ncclAllGather(d_handles + rank, d_handles, sizeof(mine), ncclChar, s->comm, nullptr);
+            ipc_ok = r == ncclSuccess && cudaStreamSynchronize(nullptr) == cudaSuccess;
+            if (ipc_ok) cudaMemcpy(all.data(), d_handles, sizeof(mine) * world, cudaMemcpyDeviceToHost);
+        }
+        // every rank must take the same decision: agree on success with an all-reduce(min)
+        int* d_ok = reinterpret_cast<int*>(s->d_flag) + 8;
+        int flag = ipc_ok ? 1 : 0;
+        if (ipc_ok) {
+            for (int r = 0; r < world && flag; ++r) {
+                if (r == rank) continue;
+                if (cudaIpcOpenMemHandle(&s->peer_recv[r], all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    s->peer_recv[r] = nullptr;
+                    flag = 0;
+                }
+            }
+        }
+        cudaMemcpy(d_ok, &flag, sizeof(int), cudaMemcpyHostToDevice);
+        if (ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, s->comm, nullptr) != ncclSuccess ||
+            cudaStreamSynchronize(nullptr) != cudaSuccess) {
+            cudaFree(d_handles);
+            osb200_sharded_destroy(s);
+            return OSB200_ERR_NCCL;
+        }
+        cudaMemcpy(&flag, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+        s->fused = flag == 1;
+        cudaFree(d_handles);
+        cudaGetLastError();
+    }
+    if (!s->fused && world > 1) {
+        if (cudaMalloc(&s->send_buf, max_n_local * sizeof(uint32_t)) != cudaSuccess) { osb200_sharded_destroy(s); return OSB200_ERR_ALLOC; }
+    }
+    *out = s;
+    return OSB200_OK;
+}
+
+// 0 = staged (NCCL send/recv), 1 = fused NVLink scatter.  Must be called identically on every rank.
+OSB200_API int osb200_sharded_set_fused(osb200_sharded_handle h, int fused)
+{
+    if (!h) return OSB200_ERR_INVALID_ARG;
+    if (fused) {
+        for (int r = 0; r < h->world; ++r) if (!h->peer_recv[r]) return OSB200_ERR_UNSUPPORTED;
+        h->fused = true;
+        return OSB200_OK;
+    }
+    if (!h->send_buf && cudaMalloc(&h->send_buf, h->max_n_local * sizeof(uint32_t)) != cudaSuccess) return OSB200_ERR_ALLOC;
+    h->fused = false;
+    return OSB200_OK;
+}
+
+OSB200_API int osb200_sharded_local_handle(osb200_sharded_handle h, osb200_handle* exch, osb200_handle* local)
+{
+    if (!h) return OSB200_ERR_INVALID_ARG;
+    if (exch) *exch = h->exch;
+    if (local) *local = h->local;
+    return OSB200_OK;
+}
+
+int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys_local, uint64_t n_local,
+                                 uint32_t** d_out, uint64_t* n_out, void* stream)
+{
+    if (!h || !d_out || !n_out || (n_local && !d_keys_local)) return OSB200_ERR_INVALID_ARG;
+    if (n_local > h->max_n_local) return OSB200_ERR_SIZE;
+    cudaStream_t q = static_cast<cudaStream_t>(stream);
+    const int R = h->world;
+
+    OSB_TRY(cudaEventRecord(h->ev[0], q));
+    // 1-2. most-significant-digit histogram, all-gather
+    int st = osb_internal_digit_histogram(h->exch, d_keys_local, n_local, 24, h->d_hist, q);
+    if (st != OSB200_OK) return st;
+    OSB_NCCL(ncclAllGather(h->d_hist, h->d_hist_all, kRadix, ncclUint64, h->comm, q));
+    OSB_TRY(cudaMemcpyAsync(h->h_hist_all, h->d_hist_all, static_cast<size_t>(R) * kRadix * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, q));
+    OSB_TRY(cudaStreamSynchronize(q));  // the plan (and the receive size) is needed on the host
+
+    // 3. plan
+    int32_t dest[kRadix];
+    uint64_t recv_count[kMaxWorld], recv_off[kRadix];
+    st = osb200_sharded_plan(reinterpret_cast<const uint64_t*>(h->h_hist_all), R, h->rank, dest, recv_count, recv_off);
+    if (st != OSB200_OK) return st;
+    const uint64_t mine = recv_count[h->rank];
+    if (mine > h->capacity) return OSB200_ERR_SIZE;  // bucket imbalance beyond the slack chosen at create
+    OSB_TRY(cudaEventRecord(h->ev[1], q));
+
+    // 4. exchange
+    if (R == 1) {
+        OSB_TRY(cudaMemcpyAsync(h->recv_buf, d_keys_local, n_local * sizeof(uint32_t), cudaMemcpyDeviceToDevice, q));
+    } else if (h->fused) {
+        // all ranks have finished reading their receive buffers from the previous call before anyone writes
+        OSB_NCCL(ncclAllReduce(h->d_flag, h->d_flag, 1, ncclUint32, ncclSum, h->comm, q));
+        for (int d = 0; d < kRadix; ++d) {
+            const unsigned long long peer = reinterpret_cast<unsigned long long>(h->peer_recv[dest[d]]);
+            h->h_out_base[d] = peer / sizeof(uint32_t) + recv_off[d];  // virtual element index relative to address 0
+        }
+        OSB_TRY(cudaMemcpyAsync(h->d_out_base, h->h_out_base, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+        st = osb_internal_binning_pass(h->exch, d_keys_local, nullptr, n_local, 24, h->d_hist, h->d_out_base, q);
+        if (st != OSB200_OK) return st;
+        // every rank's scatter kernel has completed (and its NVLink stores are performed) before any local sort starts
+        OSB_NCCL(ncclAllReduce(h->d_flag, h->d_flag, 1, ncclUint32, ncclSum, h->comm, q));
+    } else {
+        st = osb_internal_binning_pass(h->exch, d_keys_local, h->send_buf, n_local, 24, h->d_hist, nullptr, q);
+        if (st != OSB200_OK) return st;
+        // send_buf is bucket-major; the buckets of destination p are contiguous.  Receive source-major.
+        uint64_t send_off[kMaxWorld + 1] = {}, send_cnt[kMaxWorld] = {}, roff[kMaxWorld + 1] = {};
+        const unsigned long long* my_hist = h->h_hist_all + static_cast<size_t>(h->rank) * kRadix;
+        for (int d = 0; d < kRadix; ++d) send_cnt[dest[d]] += my_hist[d];
+        for (int p = 0; p < R; ++p) send_off[p + 1] = send_off[p] + send_cnt[p];
+        for (int src = 0; src < R; ++src) {
+            uint64_t c = 0;
+            for (int d = 0; d < kRadix; ++d) if (dest[d] == h->rank) c += h->h_hist_all[static_cast<size_t>(src) * kRadix + d];
+            roff[src + 1] = roff[src] + c;
+        }
+        OSB_NCCL(ncclGroupStart());
+        for (int p = 0; p < R; ++p) {
+            if (send_cnt[p]) OSB_NCCL(ncclSend(h->send_buf + send_off[p], send_cnt[p], ncclUint32, p, h->comm, q));
+            if (roff[p + 1] - roff[p]) OSB_NCCL(ncclRecv(h->recv_buf + roff[p], roff[p + 1] - roff[p], ncclUint32, p, h->comm, q));
+        }
+        OSB_NCCL(ncclGroupEnd());
+    }
+    OSB_TRY(cudaEventRecord(h->ev[2], q));
+
+    // 5. local OneSweep
+    st = osb200_sort_keys_u32(h->local, h->recv_buf, mine, q);
+    if (st != OSB200_OK) return st;
+    OSB_TRY(cudaEventRecord(h->ev[3], q));
+    *d_out = h->recv_buf;
+    *n_out = mine;
+    return OSB200_OK;
+}
+
+int osb200_sharded_last_timing(osb200_sharded_handle h, float* out_ms4)
+{
+    if (!h || !out_ms4) return OSB200_ERR_INVALID_ARG;
+    OSB_TRY(cudaEventSynchronize(h->ev[3]));
+    OSB_TRY(cudaEventElapsedTime(&out_ms4[0], h->ev[0], h->ev[1]));
+    OSB_TRY(cudaEventElapsedTime(&out_ms4[1], h->ev[1], h->ev[2]));
+    OSB_TRY(cudaEventElapsedTime(&out_ms4[2], h->ev[2], h->ev[3]));
+    OSB_TRY(cudaEventElapsedTime(&out_ms4[3], h->ev[0], h->ev[3]));
+    return OSB200_OK;
+}
+
+}  // extern "C"

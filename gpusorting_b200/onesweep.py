@@ -82,6 +82,14 @@ class OneSweepSorter:
             raise KeyError(key)
         return int(v)
 
+    def last_profile(self):
+        """Per-kernel milliseconds of the last sort when option 'profile' is on: [hist, scan, pass0, pass1, ...]."""
+        buf = (ctypes.c_float * 16)()
+        k = lib.osb200_get_profile(self._h, buf, 16)
+        if k < 0:
+            check(k, "osb200_get_profile")
+        return [float(buf[i]) for i in range(k)]
+
     # -- device sorts -------------------------------------------------------------------------------
     def sort_keys(self, keys: torch.Tensor, n: Optional[int] = None, stream=None) -> torch.Tensor:
         n = keys.numel() if n is None else int(n)

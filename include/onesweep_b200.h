@@ -120,7 +120,11 @@ OSB200_API int osb200_init_random_u32(uint32_t* d_keys, uint32_t* d_payload, uin
  * Sort/OneSweep.cu:17-42).  Keys: "rank_mode" 0=atomic-ranked (default) 1=ballot-ranked;
  * "variant" kernel variant id; returns OSB200_ERR_INVALID_ARG for unknown keys/values. */
 OSB200_API int osb200_set_option(osb200_handle h, const char* key, int64_t value);
-OSB200_API int64_t osb200_get_info(osb200_handle h, const char* key); /* "tile_keys","launches_per_sort","sm_count",... ; <0 if unknown */
+OSB200_API int64_t osb200_get_info(osb200_handle h, const char* key);
+/* With option "profile"=1 every sort records CUDA events on its stream between its kernels.  Returns the number of
+ * intervals written (waits for the last sort): out_ms[0]=GlobalHistogram, [1]=Scan, [2+p]=DigitBinningPass p.
+ * (The reference times only the whole dispatch, OneSweepDispatcher.cuh:221-224.) */
+OSB200_API int osb200_get_profile(osb200_handle h, float* out_ms, int capacity); /* "tile_keys","launches_per_sort","sm_count",... ; <0 if unknown */
 
 /* ------------------------------------------------------------------------------------------------
  * Multi-GPU sharded sort (one process per GPU).  No reference equivalent (the reference is single

@@ -37,7 +37,7 @@ def main():
         g.init_random(src, 0, 10)
         work = torch.empty_like(src)
         s = g.OneSweepSorter(n, 4, 0)
-        VARIANTS = [int(x) for x in os.environ.get("OSB_VARIANTS", "0,1").split(",")]
+        VARIANTS = [int(x) for x in os.environ.get("OSB_VARIANTS", "0,1,2").split(",")]
         MODES = [int(x) for x in os.environ.get("OSB_MODES", "0").split(",")]
         hist_ms, _ = time_ms(lambda: s.global_histogram(src))
         print(f"n=2^{e} global_histogram(+memset) {hist_ms:.3f} ms ({4*n/hist_ms/1e6:.0f} GB/s read)", flush=True)
