@@ -671,24 +671,27 @@ lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint
     }
 }
 
-template <typename KeyT, int K, int WARPS>
+template <typename KeyT, bool PAIRS, int K, int WARPS>
 struct WideSmem {
     static constexpr int THREADS = WARPS * 32;
     static constexpr int T = THREADS * K;
-    alignas(16) KeyT sorted[T];          // digit-sorted tile
-    uint32_t hist[WARPS * kRadix];       // warp-private digit counters (counts, then running slots)
-    unsigned long long off[kRadix];      // per digit: out index of tile slot 0 "as if" of this digit
+    alignas(16) KeyT sorted[T];                // digit-sorted tile
+    alignas(16) uint32_t sorted_val[PAIRS ? T : 4];  // payloads in the same order
+    alignas(16) uint32_t hist[WARPS * kRadix];  // warp-private digit counters (counts, then running slots)
+    unsigned long long keyptr[kRadix];          // per digit: byte address of out[first key of the digit - tile slot]
+    unsigned long long valptr[PAIRS ? kRadix : 1];
     uint32_t wtot[kRadix / 32];
     uint32_t tile;
 };
 
-template <typename KeyT, int K, int WARPS, int RANK_MODE, int LOOK, int STEP>
+template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP>
 __global__ void __launch_bounds__(WARPS * 32, 2)
-digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, uint64_t n, uint32_t shift,
+digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, const uint32_t* __restrict__ in_val,
+                          uint32_t* __restrict__ out_val, uint64_t n, uint32_t shift,
                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
                           uint32_t* ticket, uint32_t epoch)
 {
-    using S = WideSmem<KeyT, K, WARPS>;
+    using S = WideSmem<KeyT, PAIRS, K, WARPS>;
     constexpr int THREADS = S::THREADS;
     constexpr int T = S::T;
     static_assert(T <= 16384, "agg16 holds 15-bit counts");
@@ -699,7 +702,10 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, u
     const uint32_t lt = lanemask_lt();
     uint32_t* wh = sm.hist + warp * kRadix;
 
-    for (int i = tid; i < WARPS * kRadix; i += THREADS) sm.hist[i] = 0;
+    {
+        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+        for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+    }
     if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = sm.tile;
@@ -709,15 +715,21 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, u
 
     // ---- load (warp-striped: every warp instruction reads one contiguous 128 B / 256 B row) ------------
     KeyT key[K];
+    uint32_t val[PAIRS ? K : 1];
     const uint32_t warp_off = warp * (32 * K) + lane;
     if (full) {
 #pragma unroll
         for (int i = 0; i < K; ++i) key[i] = ld_stream(in + tile_base + warp_off + i * 32);
+        if constexpr (PAIRS) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) val[i] = ld_stream(in_val + tile_base + warp_off + i * 32);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             const uint32_t idx = warp_off + i * 32;
             key[i] = idx < valid ? in[tile_base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));  // pad: ranks last
+            if constexpr (PAIRS) val[i] = idx < valid ? in_val[tile_base + idx] : 0u;
         }
     }
 
@@ -743,61 +755,62 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, u
 
     // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -----------------
 #pragma unroll
-    for (int i = 0; i < K; ++i) sm.sorted[warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt)] = key[i];
+    for (int i = 0; i < K; ++i) {
+        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
+        sm.sorted[slot] = key[i];
+        if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
+    }
 
     // ---- chained scan with decoupled lookback ------------------------------------------------------------
     if (tid < kRadix) {
         const unsigned long long excl = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch, gbase);
         st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
                            desc_pack(epoch, kFlagInclusive, excl + tile_count));
-        sm.off[tid] = excl - tile_excl;
+        const unsigned long long first = excl - tile_excl;  // element index (relative to out) of tile slot 0
+        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
+        if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
     }
     __syncthreads();
 
     // ---- scatter -----------------------------------------------------------------------------------------
-    if (full) {
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const uint32_t idx = j * THREADS + tid;
+    for (int j = 0; j < K; ++j) {
+        const uint32_t idx = j * THREADS + tid;
+        if (full || idx < valid) {
             const KeyT k = sm.sorted[idx];
-            st_stream(out + (sm.off[digit_of(k, shift)] + idx), k);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const uint32_t idx = j * THREADS + tid;
-            if (idx < valid) {
-                const KeyT k = sm.sorted[idx];
-                st_stream(out + (sm.off[digit_of(k, shift)] + idx), k);
-            }
+            const uint32_t d = digit_of(k, shift);
+            st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
+            if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
         }
     }
 }
 
-template <typename KeyT> struct WideGeom;
-template <> struct WideGeom<uint32_t> { static constexpr int K = 32, WARPS = 16; };
-template <> struct WideGeom<uint64_t> { static constexpr int K = 16, WARPS = 16; };
+template <typename KeyT, bool PAIRS> struct WideGeom;
+template <> struct WideGeom<uint32_t, false> { static constexpr int K = 32, WARPS = 16; };
+template <> struct WideGeom<uint32_t, true>  { static constexpr int K = 16, WARPS = 16; };
+template <> struct WideGeom<uint64_t, false> { static constexpr int K = 16, WARPS = 16; };
 constexpr int kWideLook = 16, kWideStep = 8;
 
-template <typename KeyT, int RANK_MODE>
-static cudaError_t launch_wide_variant(const void* in, void* out, uint64_t n, uint32_t shift, const unsigned long long* gbase,
-                                       uint16_t* agg16, uint64_t* incl64, uint32_t* ticket, uint32_t epoch, cudaStream_t stream)
+template <typename KeyT, bool PAIRS, int RANK_MODE>
+static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
+                                       uint32_t shift, const unsigned long long* gbase, uint16_t* agg16, uint64_t* incl64,
+                                       uint32_t* ticket, uint32_t epoch, cudaStream_t stream)
 {
-    using G = WideGeom<KeyT>;
-    using S = WideSmem<KeyT, G::K, G::WARPS>;
+    using G = WideGeom<KeyT, PAIRS>;
+    using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
     const uint64_t tiles = (n + S::T - 1) / S::T;
-    auto kern = digit_binning_wide_kernel<KeyT, G::K, G::WARPS, RANK_MODE, kWideLook, kWideStep>;
+    auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, kWideLook, kWideStep>;
     kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
-        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), n, shift, gbase, agg16, incl64, ticket, epoch);
+        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch);
     return cudaGetLastError();
 }
 
-template <typename KeyT, int RANK_MODE>
+template <typename KeyT, bool PAIRS, int RANK_MODE>
 static cudaError_t set_wide_attr()
 {
-    using G = WideGeom<KeyT>;
-    using S = WideSmem<KeyT, G::K, G::WARPS>;
-    return cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, G::K, G::WARPS, RANK_MODE, kWideLook, kWideStep>,
+    using G = WideGeom<KeyT, PAIRS>;
+    using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
+    return cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, kWideLook, kWideStep>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
 }
 
@@ -832,9 +845,11 @@ static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t
 
 uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
 {
-    if (cfg.variant == kVariantWide && !pairs)
-        return key_bytes == 8 ? WideSmem<uint64_t, WideGeom<uint64_t>::K, WideGeom<uint64_t>::WARPS>::T
-                              : WideSmem<uint32_t, WideGeom<uint32_t>::K, WideGeom<uint32_t>::WARPS>::T;
+    if (cfg.variant == kVariantWide) {
+        if (key_bytes == 8) return WideGeom<uint64_t, false>::K * WideGeom<uint64_t, false>::WARPS * 32;
+        return pairs ? WideGeom<uint32_t, true>::K * WideGeom<uint32_t, true>::WARPS * 32
+                     : WideGeom<uint32_t, false>::K * WideGeom<uint32_t, false>::WARPS * 32;
+    }
     if (key_bytes == 8) return TileGeom<uint64_t, false>::WARPS * 32 * TileGeom<uint64_t, false>::K;
     if (pairs) return TileGeom<uint32_t, true>::WARPS * 32 * TileGeom<uint32_t, true>::K;
     return TileGeom<uint32_t, false>::WARPS * 32 * TileGeom<uint32_t, false>::K;
@@ -866,10 +881,12 @@ cudaError_t configure_kernels()
     if ((e = set_persistent_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_persistent_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_persistent_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, kRankAtomic>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, true, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, true, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint64_t, false, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint64_t, false, kRankBallot>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -880,13 +897,16 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
-    if (cfg.variant == kVariantWide && !pairs) {
-        if (key_bytes == 4)
-            return ballot ? launch_wide_variant<uint32_t, kRankBallot>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, stream)
-                          : launch_wide_variant<uint32_t, kRankAtomic>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, stream);
-        if (key_bytes == 8)
-            return ballot ? launch_wide_variant<uint64_t, kRankBallot>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, stream)
-                          : launch_wide_variant<uint64_t, kRankAtomic>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, stream);
+    if (cfg.variant == kVariantWide) {
+#define OSB_WIDE(KEYT, PAIRS)                                                                                          \
+    (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
+                                                           ticket, epoch, stream)                                      \
+            : launch_wide_variant<KEYT, PAIRS, kRankAtomic>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
+                                                           ticket, epoch, stream))
+        if (key_bytes == 4) return pairs ? OSB_WIDE(uint32_t, true) : OSB_WIDE(uint32_t, false);
+        if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false);
+#undef OSB_WIDE
+        return cudaErrorInvalidValue;
     }
     if (cfg.variant == kVariantPersistent && !pairs) {
         if (key_bytes == 4)

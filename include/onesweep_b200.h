@@ -149,6 +149,18 @@ OSB200_API int osb200_sharded_create(osb200_sharded_handle* out, const void* uni
 OSB200_API int osb200_sharded_destroy(osb200_sharded_handle h);
 OSB200_API int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys_local, uint64_t n_local,
                                  uint32_t** d_out, uint64_t* n_out, void* stream);
+/* The host-side exchange plan, a pure function of the all-gathered histograms (exported so the N>1 logic can be
+ * tested on CPU): dest[256] = owner rank of every most-significant-digit bucket (contiguous, non-decreasing,
+ * balanced on the global counts); recv_count[world] = keys every rank ends up with; recv_off[256] = for source
+ * `rank`, the element offset inside dest[d]'s receive buffer where its bucket-d keys go (bucket-major,
+ * source-rank-minor: the globally stable order of the MSD partition). */
+OSB200_API int osb200_sharded_plan(const uint64_t* hist_all /*[world][256]*/, int world, int rank, int32_t* dest,
+                                   uint64_t* recv_count, uint64_t* recv_off);
+/* 1 (default when CUDA IPC peer mapping works) = the exchange is the DigitBinningPass kernel scattering straight into
+ * the peers' receive buffers over NVLink; 0 = staged: local pass + ncclSend/ncclRecv.  Same value on every rank. */
+OSB200_API int osb200_sharded_set_fused(osb200_sharded_handle h, int fused);
+/* The two single-GPU sorters inside a sharded sorter (exchange pass / local sort), e.g. to set options. */
+OSB200_API int osb200_sharded_local_handle(osb200_sharded_handle h, osb200_handle* exch, osb200_handle* local);
 /* Milliseconds of the phases of the last sharded sort on this rank: [0]=histogram+allgather,
  * [1]=exchange, [2]=local sort, [3]=total (device time, CUDA events). */
 OSB200_API int osb200_sharded_last_timing(osb200_sharded_handle h, float* out_ms4);

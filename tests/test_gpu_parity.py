@@ -9,7 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-DEFAULT_VARIANT = 0
+DEFAULT_VARIANT = 2
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_onesweep_golden.json")
 
