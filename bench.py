@@ -250,7 +250,7 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": result["kernel"], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
-                "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                "traffic": (round(traffic["traffic_over_algorithmic"] * ALG_BYTES_PER_KEY_PER_PASS * n) if traffic else None),
                 "traffic_note": (traffic or {}).get("note", "no ncu capture committed for this kernel yet"),
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_KEY_PER_PASS * n,
                 "launch_ms": round(pass_ms, 4), "peak_source": peak_src,

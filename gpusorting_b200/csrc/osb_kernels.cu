@@ -684,8 +684,8 @@ struct WideSmem {
     uint32_t tile;
 };
 
-template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, const uint32_t* __restrict__ in_val,
                           uint32_t* __restrict__ out_val, uint64_t n, uint32_t shift,
                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
@@ -773,44 +773,59 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     __syncthreads();
 
     // ---- scatter -----------------------------------------------------------------------------------------
+    if (full) {  // branch-free: all shared loads of the unrolled body can be in flight together
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const uint32_t idx = j * THREADS + tid;
-        if (full || idx < valid) {
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
             const KeyT k = sm.sorted[idx];
             const uint32_t d = digit_of(k, shift);
             st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
             if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
         }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            if (idx < valid) {
+                const KeyT k = sm.sorted[idx];
+                const uint32_t d = digit_of(k, shift);
+                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
+                if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
+            }
+        }
     }
 }
 
-template <typename KeyT, bool PAIRS> struct WideGeom;
-template <> struct WideGeom<uint32_t, false> { static constexpr int K = 32, WARPS = 16; };
-template <> struct WideGeom<uint32_t, true>  { static constexpr int K = 16, WARPS = 16; };
-template <> struct WideGeom<uint64_t, false> { static constexpr int K = 16, WARPS = 16; };
-constexpr int kWideLook = 16, kWideStep = 8;
+// GEOM 0: the default geometry; GEOM 1 ("narrow"): 8,192-key tiles, three CTAs per SM (u32 keys only) -- an
+// occupancy experiment selectable as variant 3.
+template <typename KeyT, bool PAIRS, int GEOM> struct WideGeom;
+template <> struct WideGeom<uint32_t, false, 0> { static constexpr int K = 32, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
+template <> struct WideGeom<uint32_t, true, 0>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
+template <> struct WideGeom<uint64_t, false, 0> { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
+template <> struct WideGeom<uint32_t, false, 1> { static constexpr int K = 16, WARPS = 16, MINB = 3, LOOK = 32, STEP = 8; };
+template <> struct WideGeom<uint32_t, true, 1>  : WideGeom<uint32_t, true, 0> {};
+template <> struct WideGeom<uint64_t, false, 1> : WideGeom<uint64_t, false, 0> {};
 
-template <typename KeyT, bool PAIRS, int RANK_MODE>
+template <typename KeyT, bool PAIRS, int RANK_MODE, int GEOM>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
                                        uint32_t shift, const unsigned long long* gbase, uint16_t* agg16, uint64_t* incl64,
                                        uint32_t* ticket, uint32_t epoch, cudaStream_t stream)
 {
-    using G = WideGeom<KeyT, PAIRS>;
+    using G = WideGeom<KeyT, PAIRS, GEOM>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
     const uint64_t tiles = (n + S::T - 1) / S::T;
-    auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, kWideLook, kWideStep>;
+    auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>;
     kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
         static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch);
     return cudaGetLastError();
 }
 
-template <typename KeyT, bool PAIRS, int RANK_MODE>
+template <typename KeyT, bool PAIRS, int RANK_MODE, int GEOM>
 static cudaError_t set_wide_attr()
 {
-    using G = WideGeom<KeyT, PAIRS>;
+    using G = WideGeom<KeyT, PAIRS, GEOM>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
-    return cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, kWideLook, kWideStep>,
+    return cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
 }
 
@@ -845,10 +860,11 @@ static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t
 
 uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
 {
-    if (cfg.variant == kVariantWide) {
-        if (key_bytes == 8) return WideGeom<uint64_t, false>::K * WideGeom<uint64_t, false>::WARPS * 32;
-        return pairs ? WideGeom<uint32_t, true>::K * WideGeom<uint32_t, true>::WARPS * 32
-                     : WideGeom<uint32_t, false>::K * WideGeom<uint32_t, false>::WARPS * 32;
+    if (cfg.variant == kVariantWide || cfg.variant == kVariantWideNarrow) {
+        if (key_bytes == 8) return WideGeom<uint64_t, false, 0>::K * WideGeom<uint64_t, false, 0>::WARPS * 32;
+        if (pairs) return WideGeom<uint32_t, true, 0>::K * WideGeom<uint32_t, true, 0>::WARPS * 32;
+        return cfg.variant == kVariantWideNarrow ? WideGeom<uint32_t, false, 1>::K * WideGeom<uint32_t, false, 1>::WARPS * 32
+                                                 : WideGeom<uint32_t, false, 0>::K * WideGeom<uint32_t, false, 0>::WARPS * 32;
     }
     if (key_bytes == 8) return TileGeom<uint64_t, false>::WARPS * 32 * TileGeom<uint64_t, false>::K;
     if (pairs) return TileGeom<uint32_t, true>::WARPS * 32 * TileGeom<uint32_t, true>::K;
@@ -881,12 +897,14 @@ cudaError_t configure_kernels()
     if ((e = set_persistent_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_persistent_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_persistent_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, false, kRankAtomic>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, false, kRankBallot>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, true, kRankAtomic>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, true, kRankBallot>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint64_t, false, kRankAtomic>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint64_t, false, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankAtomic, 0>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankBallot, 0>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, true, kRankAtomic, 0>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, true, kRankBallot, 0>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint64_t, false, kRankAtomic, 0>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint64_t, false, kRankBallot, 0>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankAtomic, 1>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankBallot, 1>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -897,14 +915,15 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
-    if (cfg.variant == kVariantWide) {
-#define OSB_WIDE(KEYT, PAIRS)                                                                                          \
-    (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
-                                                           ticket, epoch, stream)                                      \
-            : launch_wide_variant<KEYT, PAIRS, kRankAtomic>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
-                                                           ticket, epoch, stream))
-        if (key_bytes == 4) return pairs ? OSB_WIDE(uint32_t, true) : OSB_WIDE(uint32_t, false);
-        if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false);
+    if (cfg.variant == kVariantWide || cfg.variant == kVariantWideNarrow) {
+#define OSB_WIDE(KEYT, PAIRS, GEOM)                                                                                       \
+    (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot, GEOM>(in, out, in_val, out_val, n, shift, gbase_place, agg16,   \
+                                                                 desc, ticket, epoch, stream)                              \
+            : launch_wide_variant<KEYT, PAIRS, kRankAtomic, GEOM>(in, out, in_val, out_val, n, shift, gbase_place, agg16,   \
+                                                                 desc, ticket, epoch, stream))
+        if (key_bytes == 4 && !pairs) return cfg.variant == kVariantWideNarrow ? OSB_WIDE(uint32_t, false, 1) : OSB_WIDE(uint32_t, false, 0);
+        if (key_bytes == 4) return OSB_WIDE(uint32_t, true, 0);
+        if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false, 0);
 #undef OSB_WIDE
         return cudaErrorInvalidValue;
     }
