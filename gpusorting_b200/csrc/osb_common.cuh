@@ -27,7 +27,7 @@ constexpr uint32_t kEpochMax = (1u << 24) - 1;
 
 __host__ __device__ __forceinline__ uint64_t desc_pack(uint32_t epoch, uint64_t flag, uint64_t value)
 {
-    return (static_cast<uint64_t>(epoch) << kEpochShift) | (value << 2) | flag;
+    return (static_cast<uint64_t>(epoch) << kEpochShift) | ((value & ((1ull << kValueBits) - 1)) << 2) | flag;
 }
 __host__ __device__ __forceinline__ uint64_t desc_value(uint64_t d) { return (d >> 2) & ((1ull << kValueBits) - 1); }
 __host__ __device__ __forceinline__ uint32_t desc_epoch(uint64_t d) { return static_cast<uint32_t>(d >> kEpochShift); }

@@ -261,7 +261,7 @@ lookback_and_publish(uint64_t* desc, uint32_t tile, uint32_t d, uint32_t tile_co
     unsigned long long excl = 0;
     int64_t k = static_cast<int64_t>(tile) - 1;
     while (true) {
-        if (k < 0) { excl += gbase[d]; break; }
+        if (k < 0) break;
         const uint64_t v = ld_relaxed_gpu_u64(desc + static_cast<uint64_t>(k) * kRadix + d);
         const uint64_t flag = v & kFlagMask;
         if (desc_epoch(v) != epoch || flag == kFlagNotReady) { __nanosleep(20); continue; }
@@ -269,8 +269,10 @@ lookback_and_publish(uint64_t* desc, uint32_t tile, uint32_t d, uint32_t tile_co
         if (flag == kFlagInclusive) break;
         --k;
     }
+    // descriptors carry counts relative to the start of the array (< n <= 2^38); the global digit base -- which in the
+    // sharded exchange pass is a peer ADDRESS, far larger than the value field -- is added only to the result
     st_relaxed_gpu_u64(mine, desc_pack(epoch, kFlagInclusive, excl + tile_count));
-    return excl;
+    return excl + gbase[d];
 }
 
 // =====================================================================================================
@@ -628,17 +630,19 @@ __device__ __forceinline__ void st_relaxed_gpu_u16(uint16_t* p, uint32_t v)
 }
 
 // Decoupled lookback over the compact reductions.  Examines up to LOOK predecessors per round trip, with an
-// inclusive-prefix probe every STEP tiles.  Returns the exclusive global prefix of (tile, digit d).
+// inclusive-prefix probe every STEP tiles.  Returns the number of keys with digit d in all predecessor tiles
+// (relative to the start of the array: the global digit base is added by the caller, so descriptor values stay
+// below n even when the bases are peer addresses in the sharded exchange pass).
 template <int LOOK, int STEP>
 __device__ __forceinline__ unsigned long long
 lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d, uint32_t epoch,
-              const unsigned long long* __restrict__ gbase)
+              const unsigned long long* __restrict__ /*gbase*/)
 {
     static_assert(LOOK % STEP == 0, "probe spacing must divide the window");
     unsigned long long sum = 0;                       // reductions of tiles (cur, tile-1] already added
     int64_t cur = static_cast<int64_t>(tile) - 1;     // nearest predecessor not yet accounted for
     while (true) {
-        if (cur < 0) return sum + gbase[d];
+        if (cur < 0) return sum;
         uint32_t a[LOOK];
         uint64_t c[LOOK / STEP];
 #pragma unroll
@@ -657,7 +661,7 @@ lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint
 #pragma unroll
         for (int i = 0; i < LOOK; ++i) {
             const int64_t t = cur - i;
-            if (t < 0) return run + gbase[d];
+            if (t < 0) return run;
             if ((i % STEP) == STEP - 1) {
                 const uint64_t v = c[i / STEP];
                 if (desc_epoch(v) == epoch && (v & kFlagMask) == kFlagInclusive) return run + desc_value(v);
@@ -694,7 +698,7 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     using S = WideSmem<KeyT, PAIRS, K, WARPS>;
     constexpr int THREADS = S::THREADS;
     constexpr int T = S::T;
-    static_assert(T <= 16384, "agg16 holds 15-bit counts");
+    static_assert(T < 32768, "agg16 holds 15-bit counts");
     extern __shared__ __align__(16) unsigned char s_raw[];
     S& sm = *reinterpret_cast<S*>(s_raw);
 
@@ -763,10 +767,10 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
 
     // ---- chained scan with decoupled lookback ------------------------------------------------------------
     if (tid < kRadix) {
-        const unsigned long long excl = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch, gbase);
+        const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch, gbase);
         st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
-                           desc_pack(epoch, kFlagInclusive, excl + tile_count));
-        const unsigned long long first = excl - tile_excl;  // element index (relative to out) of tile slot 0
+                           desc_pack(epoch, kFlagInclusive, prior + tile_count));
+        const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
         sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
         if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
     }
@@ -805,6 +809,8 @@ template <> struct WideGeom<uint64_t, false, 0> { static constexpr int K = 16, W
 template <> struct WideGeom<uint32_t, false, 1> { static constexpr int K = 16, WARPS = 16, MINB = 3, LOOK = 32, STEP = 8; };
 template <> struct WideGeom<uint32_t, true, 1>  : WideGeom<uint32_t, true, 0> {};
 template <> struct WideGeom<uint64_t, false, 1> : WideGeom<uint64_t, false, 0> {};
+// GEOM 2 ("single"): one 1024-thread CTA per SM, 31,744-key tiles (u32 keys only) -- halves the lookback window again
+template <> struct WideGeom<uint32_t, false, 2> { static constexpr int K = 31, WARPS = 32, MINB = 1, LOOK = 8, STEP = 4; };
 
 template <typename KeyT, bool PAIRS, int RANK_MODE, int GEOM>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
@@ -860,9 +866,10 @@ static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t
 
 uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
 {
-    if (cfg.variant == kVariantWide || cfg.variant == kVariantWideNarrow) {
+    if (cfg.variant == kVariantWide || cfg.variant == kVariantWideNarrow || cfg.variant == kVariantWideSingle) {
         if (key_bytes == 8) return WideGeom<uint64_t, false, 0>::K * WideGeom<uint64_t, false, 0>::WARPS * 32;
         if (pairs) return WideGeom<uint32_t, true, 0>::K * WideGeom<uint32_t, true, 0>::WARPS * 32;
+        if (cfg.variant == kVariantWideSingle) return WideGeom<uint32_t, false, 2>::K * WideGeom<uint32_t, false, 2>::WARPS * 32;
         return cfg.variant == kVariantWideNarrow ? WideGeom<uint32_t, false, 1>::K * WideGeom<uint32_t, false, 1>::WARPS * 32
                                                  : WideGeom<uint32_t, false, 0>::K * WideGeom<uint32_t, false, 0>::WARPS * 32;
     }
@@ -905,6 +912,8 @@ cudaError_t configure_kernels()
     if ((e = set_wide_attr<uint64_t, false, kRankBallot, 0>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint32_t, false, kRankAtomic, 1>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint32_t, false, kRankBallot, 1>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankAtomic, 2>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankBallot, 2>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -915,13 +924,17 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
-    if (cfg.variant == kVariantWide || cfg.variant == kVariantWideNarrow) {
+    if (cfg.variant == kVariantWide || cfg.variant == kVariantWideNarrow || cfg.variant == kVariantWideSingle) {
 #define OSB_WIDE(KEYT, PAIRS, GEOM)                                                                                       \
     (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot, GEOM>(in, out, in_val, out_val, n, shift, gbase_place, agg16,   \
                                                                  desc, ticket, epoch, stream)                              \
             : launch_wide_variant<KEYT, PAIRS, kRankAtomic, GEOM>(in, out, in_val, out_val, n, shift, gbase_place, agg16,   \
                                                                  desc, ticket, epoch, stream))
-        if (key_bytes == 4 && !pairs) return cfg.variant == kVariantWideNarrow ? OSB_WIDE(uint32_t, false, 1) : OSB_WIDE(uint32_t, false, 0);
+        if (key_bytes == 4 && !pairs) {
+            if (cfg.variant == kVariantWideNarrow) return OSB_WIDE(uint32_t, false, 1);
+            if (cfg.variant == kVariantWideSingle) return OSB_WIDE(uint32_t, false, 2);
+            return OSB_WIDE(uint32_t, false, 0);
+        }
         if (key_bytes == 4) return OSB_WIDE(uint32_t, true, 0);
         if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false, 0);
 #undef OSB_WIDE
