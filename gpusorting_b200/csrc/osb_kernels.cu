@@ -800,17 +800,13 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     }
 }
 
-// GEOM 0: the default geometry; GEOM 1 ("narrow"): 8,192-key tiles, three CTAs per SM (u32 keys only) -- an
-// occupancy experiment selectable as variant 3.
+// Geometry.  Measured alternatives (n = 2^30 u32 keys, ms per pass; profiles/r01_geometry_experiments.txt):
+//   16,384-key tiles, 2 x 512 threads per SM (this one) 2.80 | 8,192-key tiles, 3 CTAs/SM 5.46 (lookback window doubles,
+//   spills) | 31,744-key tiles, 1 x 1024 threads per SM 3.15 (no second CTA to overlap barriers and the lookback wait).
 template <typename KeyT, bool PAIRS, int GEOM> struct WideGeom;
 template <> struct WideGeom<uint32_t, false, 0> { static constexpr int K = 32, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
 template <> struct WideGeom<uint32_t, true, 0>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
 template <> struct WideGeom<uint64_t, false, 0> { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
-template <> struct WideGeom<uint32_t, false, 1> { static constexpr int K = 16, WARPS = 16, MINB = 3, LOOK = 32, STEP = 8; };
-template <> struct WideGeom<uint32_t, true, 1>  : WideGeom<uint32_t, true, 0> {};
-template <> struct WideGeom<uint64_t, false, 1> : WideGeom<uint64_t, false, 0> {};
-// GEOM 2 ("single"): one 1024-thread CTA per SM, 31,744-key tiles (u32 keys only) -- halves the lookback window again
-template <> struct WideGeom<uint32_t, false, 2> { static constexpr int K = 31, WARPS = 32, MINB = 1, LOOK = 8, STEP = 4; };
 
 template <typename KeyT, bool PAIRS, int RANK_MODE, int GEOM>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
@@ -866,12 +862,10 @@ static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t
 
 uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
 {
-    if (cfg.variant == kVariantWide || cfg.variant == kVariantWideNarrow || cfg.variant == kVariantWideSingle) {
+    if (cfg.variant == kVariantWide) {
         if (key_bytes == 8) return WideGeom<uint64_t, false, 0>::K * WideGeom<uint64_t, false, 0>::WARPS * 32;
         if (pairs) return WideGeom<uint32_t, true, 0>::K * WideGeom<uint32_t, true, 0>::WARPS * 32;
-        if (cfg.variant == kVariantWideSingle) return WideGeom<uint32_t, false, 2>::K * WideGeom<uint32_t, false, 2>::WARPS * 32;
-        return cfg.variant == kVariantWideNarrow ? WideGeom<uint32_t, false, 1>::K * WideGeom<uint32_t, false, 1>::WARPS * 32
-                                                 : WideGeom<uint32_t, false, 0>::K * WideGeom<uint32_t, false, 0>::WARPS * 32;
+        return WideGeom<uint32_t, false, 0>::K * WideGeom<uint32_t, false, 0>::WARPS * 32;
     }
     if (key_bytes == 8) return TileGeom<uint64_t, false>::WARPS * 32 * TileGeom<uint64_t, false>::K;
     if (pairs) return TileGeom<uint32_t, true>::WARPS * 32 * TileGeom<uint32_t, true>::K;
@@ -910,10 +904,6 @@ cudaError_t configure_kernels()
     if ((e = set_wide_attr<uint32_t, true, kRankBallot, 0>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint64_t, false, kRankAtomic, 0>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint64_t, false, kRankBallot, 0>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, false, kRankAtomic, 1>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, false, kRankBallot, 1>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, false, kRankAtomic, 2>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, false, kRankBallot, 2>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -924,17 +914,13 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
-    if (cfg.variant == kVariantWide || cfg.variant == kVariantWideNarrow || cfg.variant == kVariantWideSingle) {
+    if (cfg.variant == kVariantWide) {
 #define OSB_WIDE(KEYT, PAIRS, GEOM)                                                                                       \
     (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot, GEOM>(in, out, in_val, out_val, n, shift, gbase_place, agg16,   \
                                                                  desc, ticket, epoch, stream)                              \
             : launch_wide_variant<KEYT, PAIRS, kRankAtomic, GEOM>(in, out, in_val, out_val, n, shift, gbase_place, agg16,   \
                                                                  desc, ticket, epoch, stream))
-        if (key_bytes == 4 && !pairs) {
-            if (cfg.variant == kVariantWideNarrow) return OSB_WIDE(uint32_t, false, 1);
-            if (cfg.variant == kVariantWideSingle) return OSB_WIDE(uint32_t, false, 2);
-            return OSB_WIDE(uint32_t, false, 0);
-        }
+        if (key_bytes == 4 && !pairs) return OSB_WIDE(uint32_t, false, 0);
         if (key_bytes == 4) return OSB_WIDE(uint32_t, true, 0);
         if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false, 0);
 #undef OSB_WIDE

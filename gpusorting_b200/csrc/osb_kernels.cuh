@@ -9,11 +9,9 @@ namespace osb {
 enum BinningVariant : int {
     kVariantTilePerCta = 0,  // one CTA per partition tile, keys loaded straight into registers
     kVariantPersistent = 1,  // persistent CTAs, TMA (cp.async.bulk) double-buffered tile staging
-    kVariantWideNarrow = 3,  // variant 2's kernel with 8,192-key tiles and three CTAs per SM (u32 keys only; experiment)
-    kVariantWideSingle = 4,  // variant 2's kernel, one 1024-thread CTA per SM, 31,744-key tiles (u32 keys only; experiment)
     kVariantWide = 2,        // 16,384-key tiles, two-phase atomic ranking, compact reductions + one-shot lookback
 };
-constexpr int kNumVariants = 5;
+constexpr int kNumVariants = 3;
 enum RankMode : int {
     kRankAtomic = 0,  // one shared-memory atomicAdd per key (lane-ordered on sm_100, verified at create)
     kRankBallot = 1,  // 8 ballots per key (the reference's warp-level multisplit, OneSweep.cu:208-253)
