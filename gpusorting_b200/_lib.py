@@ -39,6 +39,7 @@ SIGNATURES = {
     "osb200_sharded_sort_keys_u32": (c_int, [c_vp, c_vp, c_u64, ctypes.POINTER(c_vp), ctypes.POINTER(c_u64), c_vp]),
     "osb200_sharded_plan": (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "osb200_sharded_set_fused": (c_int, [c_vp, c_int]),
+    "osb200_sharded_force_fine": (c_int, [c_vp, c_int]),
     "osb200_sharded_local_handle": (c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
     "osb200_sharded_last_timing": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),
 }

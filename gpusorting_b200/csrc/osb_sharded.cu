@@ -59,6 +59,8 @@ struct osb200_sharded_sorter {
     uint32_t* d_flag = nullptr;                // 1-element all-reduce used as a stream-ordered cross-GPU barrier
     void* peer_recv[kMaxWorld] = {};           // IPC-mapped receive buffers of all ranks (own = recv_buf)
     bool fused = true;
+    bool force_fine = false;  // always use the 256-bucket plan (tests)
+    int last_bins = 0;
     cudaEvent_t ev[4] = {};
     float last_ms[4] = {0, 0, 0, 0};
 };
@@ -238,6 +240,14 @@ OSB200_API int osb200_sharded_set_fused(osb200_sharded_handle h, int fused)
     return OSB200_OK;
 }
 
+// Testing hook: 1 = always use the 256-bucket greedy plan even when the 2^k equal-width split would fit.
+OSB200_API int osb200_sharded_force_fine(osb200_sharded_handle h, int on)
+{
+    if (!h) return OSB200_ERR_INVALID_ARG;
+    h->force_fine = on != 0;
+    return OSB200_OK;
+}
+
 OSB200_API int osb200_sharded_local_handle(osb200_sharded_handle h, osb200_handle* exch, osb200_handle* local)
 {
     if (!h) return OSB200_ERR_INVALID_ARG;
@@ -263,11 +273,46 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
                             cudaMemcpyDeviceToHost, q));
     OSB_TRY(cudaStreamSynchronize(q));  // the plan (and the receive size) is needed on the host
 
-    // 3. plan
+    // 3. plan.  Preferred: R = 2^k ranks and the equal-width split of the key space fits the receive buffers ->
+    //    exchange on the top k bits only (R bins instead of 256): runs of ~n/(tiles*R) keys (8 KB at R = 8) keep the
+    //    NVLink stores full-sector (measured: 32-key misaligned runs reach ~55 % of the 128-B-aligned peer store rate,
+    //    profiles/r01_p2p_store_ub.txt) and the ranking atomics nearly conflict-free.  Otherwise: 256 buckets, greedy.
     int32_t dest[kRadix];
     uint64_t recv_count[kMaxWorld], recv_off[kRadix];
-    st = osb200_sharded_plan(reinterpret_cast<const uint64_t*>(h->h_hist_all), R, h->rank, dest, recv_count, recv_off);
-    if (st != OSB200_OK) return st;
+    uint32_t xshift = 24;  // digit position of the exchange pass
+    int bins = kRadix;
+    int k = 0;
+    while ((1 << k) < R) ++k;
+    bool coarse = R > 1 && (1 << k) == R && !h->force_fine;
+    if (coarse) {
+        const int per = kRadix >> k;
+        for (int q2 = 0; q2 < R; ++q2) recv_count[q2] = 0;
+        for (int src = 0; src < R; ++src)
+            for (int d = 0; d < kRadix; ++d) recv_count[d / per] += h->h_hist_all[static_cast<size_t>(src) * kRadix + d];
+        for (int q2 = 0; q2 < R; ++q2) coarse = coarse && recv_count[q2] <= h->capacity;
+    }
+    if (coarse) {
+        const int per = kRadix >> k;
+        xshift = 32 - k;
+        bins = R;
+        for (int b = 0; b < kRadix; ++b) { dest[b] = b < R ? b : R - 1; recv_off[b] = 0; }
+        for (int b = 0; b < R; ++b) {
+            uint64_t off = 0;
+            for (int src = 0; src < h->rank; ++src)
+                for (int d = b * per; d < (b + 1) * per; ++d) off += h->h_hist_all[static_cast<size_t>(src) * kRadix + d];
+            recv_off[b] = off;
+        }
+        // the coarse histogram of THIS rank's keys, in the layout the pass expects (bins beyond R are empty)
+        for (int b = 0; b < kRadix; ++b) h->h_out_base[b] = 0;
+        const unsigned long long* my_hist = h->h_hist_all + static_cast<size_t>(h->rank) * kRadix;
+        for (int d = 0; d < kRadix; ++d) h->h_out_base[d / per] += my_hist[d];
+        OSB_TRY(cudaMemcpyAsync(h->d_hist, h->h_out_base, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+        OSB_TRY(cudaStreamSynchronize(q));  // h_out_base is reused below
+    } else {
+        st = osb200_sharded_plan(reinterpret_cast<const uint64_t*>(h->h_hist_all), R, h->rank, dest, recv_count, recv_off);
+        if (st != OSB200_OK) return st;
+    }
+    h->last_bins = bins;
     const uint64_t mine = recv_count[h->rank];
     if (mine > h->capacity) return OSB200_ERR_SIZE;  // bucket imbalance beyond the slack chosen at create
     OSB_TRY(cudaEventRecord(h->ev[1], q));
@@ -283,21 +328,23 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
             h->h_out_base[d] = peer / sizeof(uint32_t) + recv_off[d];  // virtual element index relative to address 0
         }
         OSB_TRY(cudaMemcpyAsync(h->d_out_base, h->h_out_base, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
-        st = osb_internal_binning_pass(h->exch, d_keys_local, nullptr, n_local, 24, h->d_hist, h->d_out_base, q);
+        st = osb_internal_binning_pass(h->exch, d_keys_local, nullptr, n_local, xshift, h->d_hist, h->d_out_base, q);
         if (st != OSB200_OK) return st;
         // every rank's scatter kernel has completed (and its NVLink stores are performed) before any local sort starts
         OSB_NCCL(ncclAllReduce(h->d_flag, h->d_flag, 1, ncclUint32, ncclSum, h->comm, q));
     } else {
-        st = osb_internal_binning_pass(h->exch, d_keys_local, h->send_buf, n_local, 24, h->d_hist, nullptr, q);
+        st = osb_internal_binning_pass(h->exch, d_keys_local, h->send_buf, n_local, xshift, h->d_hist, nullptr, q);
         if (st != OSB200_OK) return st;
-        // send_buf is bucket-major; the buckets of destination p are contiguous.  Receive source-major.
+        // send_buf is bin-major; the bins of destination p are contiguous.  Receive source-major.
         uint64_t send_off[kMaxWorld + 1] = {}, send_cnt[kMaxWorld] = {}, roff[kMaxWorld + 1] = {};
+        const int per = coarse ? (kRadix >> k) : 1;
         const unsigned long long* my_hist = h->h_hist_all + static_cast<size_t>(h->rank) * kRadix;
-        for (int d = 0; d < kRadix; ++d) send_cnt[dest[d]] += my_hist[d];
+        for (int d = 0; d < kRadix; ++d) send_cnt[dest[coarse ? d / per : d]] += my_hist[d];
         for (int p = 0; p < R; ++p) send_off[p + 1] = send_off[p] + send_cnt[p];
         for (int src = 0; src < R; ++src) {
             uint64_t c = 0;
-            for (int d = 0; d < kRadix; ++d) if (dest[d] == h->rank) c += h->h_hist_all[static_cast<size_t>(src) * kRadix + d];
+            for (int d = 0; d < kRadix; ++d)
+                if (dest[coarse ? d / per : d] == h->rank) c += h->h_hist_all[static_cast<size_t>(src) * kRadix + d];
             roff[src + 1] = roff[src] + c;
         }
         OSB_NCCL(ncclGroupStart());

@@ -77,6 +77,9 @@ class ShardedSorter:
     def set_fused(self, fused: bool) -> None:
         check(lib.osb200_sharded_set_fused(self._h, 1 if fused else 0), "osb200_sharded_set_fused")
 
+    def force_fine(self, on: bool) -> None:
+        check(lib.osb200_sharded_force_fine(self._h, 1 if on else 0), "osb200_sharded_force_fine")
+
     def set_local_option(self, key: str, value: int) -> None:
         a, b = ctypes.c_void_p(), ctypes.c_void_p()
         check(lib.osb200_sharded_local_handle(self._h, ctypes.byref(a), ctypes.byref(b)), "osb200_sharded_local_handle")

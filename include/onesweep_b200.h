@@ -159,6 +159,10 @@ OSB200_API int osb200_sharded_plan(const uint64_t* hist_all /*[world][256]*/, in
 /* 1 (default when CUDA IPC peer mapping works) = the exchange is the DigitBinningPass kernel scattering straight into
  * the peers' receive buffers over NVLink; 0 = staged: local pass + ncclSend/ncclRecv.  Same value on every rank. */
 OSB200_API int osb200_sharded_set_fused(osb200_sharded_handle h, int fused);
+/* Exchange granularity: by default, when world is a power of two and the equal-width split of the key space fits the
+ * receive buffers, the exchange bins on the top log2(world) bits only (long runs, full NVLink sectors); otherwise on
+ * the top 8 bits with the greedy plan.  on=1 forces the 256-bucket plan (tests / skewed data).  Same on every rank. */
+OSB200_API int osb200_sharded_force_fine(osb200_sharded_handle h, int on);
 /* The two single-GPU sorters inside a sharded sorter (exchange pass / local sort), e.g. to set options. */
 OSB200_API int osb200_sharded_local_handle(osb200_sharded_handle h, osb200_handle* exch, osb200_handle* local);
 /* Milliseconds of the phases of the last sharded sort on this rank: [0]=histogram+allgather,

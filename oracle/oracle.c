@@ -15,6 +15,8 @@
  * Every function cites the reference file:line whose behaviour it restates
  * (paths relative to /root/reference/GPUSortingCUDA/).
  */
+#define _GNU_SOURCE
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -214,6 +216,8 @@ uint64_t orc_validate_pairs_u32(const uint32_t* keys, const uint32_t* vals, uint
  * chunk-exclusive digit offsets -- the CPU analogue of the per-tile reductions chained in
  * OneSweep.cu:257-327 -- so the scatter stays stable.  4 (or 8) passes, ping-pong as above.
  * ------------------------------------------------------------------------------------------- */
+#define ORC_WC 16 /* keys buffered per bin before a burst store (64 B for u32) */
+
 static void orc_par_pass(const void* src, void* dst, const uint32_t* sv, uint32_t* dv, uint64_t n,
                          uint32_t shift, int key_bytes, int threads, uint64_t* table /* threads*256 */)
 {
@@ -236,24 +240,50 @@ static void orc_par_pass(const void* src, void* dst, const uint32_t* sv, uint32_
             for (uint32_t d = 0; d < ORC_RADIX; ++d)
                 for (int tt = 0; tt < threads; ++tt) { uint64_t v = table[(size_t)tt * ORC_RADIX + d]; table[(size_t)tt * ORC_RADIX + d] = run; run += v; }
         }
-        if (key_bytes == 4) {
+        if (key_bytes == 4 && !sv) {
+            /* software write-combining: random 4-byte stores become 64-byte bursts (order within a bin is kept) */
             const uint32_t* s = (const uint32_t*)src; uint32_t* o = (uint32_t*)dst;
-            if (sv) for (uint64_t i = lo; i < hi; ++i) { uint64_t p = c[(s[i] >> shift) & 255u]++; o[p] = s[i]; dv[p] = sv[i]; }
-            else    for (uint64_t i = lo; i < hi; ++i) o[c[(s[i] >> shift) & 255u]++] = s[i];
+            uint32_t buf[ORC_RADIX][ORC_WC];
+            uint8_t fill[ORC_RADIX];
+            memset(fill, 0, sizeof(fill));
+            for (uint64_t i = lo; i < hi; ++i) {
+                const uint32_t k = s[i], d = (k >> shift) & 255u;
+                buf[d][fill[d]++] = k;
+                if (fill[d] == ORC_WC) { memcpy(o + c[d], buf[d], sizeof(buf[d])); c[d] += ORC_WC; fill[d] = 0; }
+            }
+            for (uint32_t d = 0; d < ORC_RADIX; ++d) { memcpy(o + c[d], buf[d], fill[d] * sizeof(uint32_t)); c[d] += fill[d]; }
+        } else if (key_bytes == 4) {
+            const uint32_t* s = (const uint32_t*)src; uint32_t* o = (uint32_t*)dst;
+            for (uint64_t i = lo; i < hi; ++i) { uint64_t p = c[(s[i] >> shift) & 255u]++; o[p] = s[i]; dv[p] = sv[i]; }
         } else {
             const uint64_t* s = (const uint64_t*)src; uint64_t* o = (uint64_t*)dst;
-            for (uint64_t i = lo; i < hi; ++i) o[c[(s[i] >> shift) & 255u]++] = s[i];
+            uint64_t buf[ORC_RADIX][ORC_WC / 2];
+            uint8_t fill[ORC_RADIX];
+            memset(fill, 0, sizeof(fill));
+            for (uint64_t i = lo; i < hi; ++i) {
+                const uint64_t k = s[i]; const uint32_t d = (uint32_t)(k >> shift) & 255u;
+                buf[d][fill[d]++] = k;
+                if (fill[d] == ORC_WC / 2) { memcpy(o + c[d], buf[d], sizeof(buf[d])); c[d] += ORC_WC / 2; fill[d] = 0; }
+            }
+            for (uint32_t d = 0; d < ORC_RADIX; ++d) { memcpy(o + c[d], buf[d], fill[d] * sizeof(uint64_t)); c[d] += fill[d]; }
         }
     }
 }
 
+/* threads the baseline may use: OpenMP's limit capped by the CPUs this process is allowed to run on */
 int orc_host_threads(void)
 {
 #ifdef _OPENMP
-    return omp_get_max_threads();
+    int t = omp_get_max_threads();
 #else
-    return 1;
+    int t = 1;
 #endif
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+        const int a = CPU_COUNT(&set);
+        if (a > 0 && a < t) t = a;
+    }
+    return t < 1 ? 1 : t;
 }
 
 /* key_bytes 4|8; vals/alt_val may be NULL (keys only). threads<=0 -> all. Result in keys(/vals). */

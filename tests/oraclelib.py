@@ -95,8 +95,8 @@ class Oracle:
         self.lib.orc_onesweep_pairs_u32(k.ctypes.data, v.ctypes.data, ak.ctypes.data, av.ctypes.data, k.size)
         return k, v
 
-    def sort_parallel_inplace(self, keys, vals=None, threads=0):
-        alt = np.empty_like(keys)
+    def sort_parallel_inplace(self, keys, vals=None, threads=0, alt=None):
+        alt = np.empty_like(keys) if alt is None else alt
         av = np.empty_like(vals) if vals is not None else None
         return self.lib.orc_onesweep_parallel(keys.ctypes.data, alt.ctypes.data,
                                               vals.ctypes.data if vals is not None else None,

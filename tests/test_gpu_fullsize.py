@@ -9,9 +9,17 @@ pytestmark = pytest.mark.gpu
 
 
 def multiset_checksum(t):
-    # order-independent: wrapping sum and xor of all elements
-    x = t.view(torch.int32).to(torch.int64)
-    return int(x.sum().item()), int(torch.bitwise_xor(x[::2][: x.numel() // 2], x[1::2][: x.numel() // 2]).sum().item())
+    """Order-independent: wrapping sums of x, x*x and x*2654435761 over all elements, in chunks to bound memory."""
+    a = b = c = 0
+    flat = t.view(torch.int32)
+    step = 1 << 28
+    for i in range(0, flat.numel(), step):
+        x = flat[i:i + step].to(torch.int64) & 0xFFFFFFFF
+        a += int(x.sum().item())
+        b += int((x * x).sum().item())          # int64 arithmetic wraps: still a function of the multiset only
+        c += int((x * 2654435761 ^ (x >> 7)).sum().item())
+    m = (1 << 64) - 1
+    return a & m, b & m, c & m
 
 
 @pytest.fixture(scope="module")

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n, fused, q):
+def _worker(rank, world, port, n, fused, fine, q):
     import sys
 
     sys.path.insert(0, ROOT)
@@ -27,6 +27,7 @@ def _worker(rank, world, port, n, fused, q):
         orc = oraclelib.load_oracle()
         s = sharded.ShardedSorter(n, slack_percent=50)
         s.set_fused(fused)
+        s.force_fine(fine)
         ok = True
         for trial, nl in enumerate([n, n - 12345, 1000 + rank, n]):
             keys = orc.init_random_u32(nl, 0, 10 + rank + 100 * trial)
@@ -52,8 +53,9 @@ def _worker(rank, world, port, n, fused, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("fine", [False, True])
 @pytest.mark.parametrize("fused", [True, False])
-def test_sharded_sort_matches_global_sort(fused):
+def test_sharded_sort_matches_global_sort(fused, fine):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -61,8 +63,8 @@ def test_sharded_sort_matches_global_sort(fused):
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 1000) + (1 if fused else 0)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, 1 << 20, fused, q)) for r in range(world)]
+    port = 29600 + (os.getpid() % 1000) + (1 if fused else 0) + (2 if fine else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 1 << 20, fused, fine, q)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
