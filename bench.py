@@ -137,7 +137,7 @@ def cpu_baseline(threads_hint: int = 0):
     }
 
 
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, rank, world, emit):
     """--impl reference: the CPU leg (rank 0 only; other ranks exit 0 without work)."""
     if rank != 0:
         return
@@ -175,10 +175,17 @@ def run_reference_arm(args, rank, world):
         "e2e": {"value": round(value, 4), "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (e.g. the NCCL version banner) go to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -195,7 +202,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, rank, world, emit)
         return
 
     import torch
@@ -268,7 +275,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -62,6 +62,7 @@ class ShardedSorter:
         self._h = h
         self.max_n_local = int(max_n_local)
         self._stage = None
+        self._host_out = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -105,7 +106,10 @@ class ShardedSorter:
             self._stage = torch.empty(self.max_n_local, dtype=torch.int32, device="cuda")
         self._stage[:n].copy_(host_keys, non_blocking=True)
         res = self.sort_keys(self._stage, n)
-        out = torch.empty(res.numel(), dtype=torch.int32, pin_memory=host_keys.is_pinned())
+        if self._host_out is None or self._host_out.numel() < res.numel():  # pinned once, reused by later calls
+            cap = max(res.numel(), self.max_n_local + self.max_n_local // 4)
+            self._host_out = torch.empty(cap, dtype=torch.int32, pin_memory=True)
+        out = self._host_out[: res.numel()]
         out.copy_(res, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out

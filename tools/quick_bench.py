@@ -64,13 +64,31 @@ def main():
             print(f"n=2^{e} REFERENCE CUDA OneSweep (sm_100a build): median {med:.3f} ms best {best:.3f} -> {n/med/1e6:.1f} Gkeys/s", flush=True)
             ref.lib.ref_destroy(h)
             del alt
-        if e <= 29:
+        if os.environ.get("OSB_SKIP_PAIRS") is None:
             sp = g.OneSweepSorter(n, 4, 4)
+            sp.set_option("profile", 1)
             v, vw = torch.arange(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
             med, best = time_ms(lambda: sp.sort_pairs(work, vw), prep=lambda: (work.copy_(src), vw.copy_(v)))
-            print(f"n=2^{e} pairs u32/u32: median {med:.3f} ms -> {n/med/1e6:.1f} Gpairs/s, {64*n/med/1e6/PEAK*100:.1f}% (64 B/pair)", flush=True)
+            pr = sp.last_profile()
+            print(f"n=2^{e} pairs u32/u32: median {med:.3f} ms -> {n/med/1e6:.1f} Gpairs/s, {64*n/med/1e6/PEAK*100:.1f}% (64 B/pair); "
+                  f"hist {pr[0]:.3f} ms, pass {sum(pr[2:])/len(pr[2:]):.3f} ms ({16*n/(sum(pr[2:])/len(pr[2:]))/1e6:.0f} GB/s)", flush=True)
+            assert sp.validate(work) == 0
             sp.close()
             del v, vw
+            torch.cuda.empty_cache()
+            s8 = g.OneSweepSorter(n, 8, 0)
+            s8.set_option("profile", 1)
+            w8 = torch.empty(2 * n, dtype=torch.int32, device="cuda")
+            g.init_random(w8, 0, 10)
+            src8 = w8.view(torch.int64)
+            work8 = torch.empty_like(src8)
+            med, best = time_ms(lambda: s8.sort_keys(work8), prep=lambda: work8.copy_(src8))
+            pr = s8.last_profile()
+            print(f"n=2^{e} keys u64: median {med:.3f} ms -> {n/med/1e6:.1f} Gkeys/s, {128*n/med/1e6/PEAK*100:.1f}% (128 B/key); "
+                  f"hist {pr[0]:.3f} ms, pass {sum(pr[2:])/len(pr[2:]):.3f} ms ({16*n/(sum(pr[2:])/len(pr[2:]))/1e6:.0f} GB/s)", flush=True)
+            assert s8.validate(work8) == 0
+            s8.close()
+            del w8, src8, work8
         del src, work
         torch.cuda.empty_cache()
 
