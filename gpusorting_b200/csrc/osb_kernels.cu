@@ -287,7 +287,7 @@ digit_binning_tile_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     constexpr int THREADS = WARPS * 32;
     constexpr int T = THREADS * K;  // keys per partition tile
     static_assert(WARPS >= 8, "need one thread per digit");
-    extern __shared__ __align__(16) unsigned char s_raw[];  // max(WARPS*256*4, T*sizeof(KeyT)) bytes
+    extern __shared__ __align__(128) unsigned char s_raw[];  // max(WARPS*256*4, T*sizeof(KeyT)) bytes
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_raw);  // [WARPS][256] during ranking
     KeyT* s_keys = reinterpret_cast<KeyT*>(s_raw);          // [T] digit-sorted tile afterwards
     uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_raw);  // [T] payloads in the same order (pairs)
@@ -686,117 +686,149 @@ struct WideSmem {
     unsigned long long valptr[PAIRS ? kRadix : 1];
     uint32_t wtot[kRadix / 32];
     uint32_t tile;
+    uint32_t tile_next;
 };
 
-template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP, int MINB>
+// PERSIST = false: one CTA per partition tile.  PERSIST = true: a resident CTA loops over tiles it draws from the ticket
+// counter and issues the global loads of its NEXT tile right after the keys of the current one have been moved to shared
+// memory, so those loads (and the ticket round trip) overlap the lookback wait and the scatter; the key registers are
+// simply reused.  Tickets are drawn and consumed in increasing order by every CTA, so the lowest unfinished tile is
+// always being processed by a resident CTA (no deadlock).
+template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP, int MINB, bool PERSIST>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, const uint32_t* __restrict__ in_val,
                           uint32_t* __restrict__ out_val, uint64_t n, uint32_t shift,
                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
-                          uint32_t* ticket, uint32_t epoch)
+                          uint32_t* ticket, uint32_t epoch, uint32_t num_tiles)
 {
     using S = WideSmem<KeyT, PAIRS, K, WARPS>;
     constexpr int THREADS = S::THREADS;
     constexpr int T = S::T;
     static_assert(T < 32768, "agg16 holds 15-bit counts");
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    extern __shared__ __align__(128) unsigned char s_raw[];
     S& sm = *reinterpret_cast<S*>(s_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
     uint32_t* wh = sm.hist + warp * kRadix;
+    const uint32_t warp_off = warp * (32 * K) + lane;
 
-    {
-        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
-        for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
-    }
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = sm.tile;
-    const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
-    const bool full = tile_base + T <= n;
-    const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
-
-    // ---- load (warp-striped: every warp instruction reads one contiguous 128 B / 256 B row) ------------
     KeyT key[K];
     uint32_t val[PAIRS ? K : 1];
-    const uint32_t warp_off = warp * (32 * K) + lane;
-    if (full) {
+    // warp-striped loads: every warp instruction reads one contiguous 128 B / 256 B row
+    auto load_tile = [&](uint32_t t) {
+        const uint64_t base = static_cast<uint64_t>(t) * T;
+        if (base + T <= n) {
 #pragma unroll
-        for (int i = 0; i < K; ++i) key[i] = ld_stream(in + tile_base + warp_off + i * 32);
-        if constexpr (PAIRS) {
+            for (int i = 0; i < K; ++i) key[i] = ld_stream(in + base + warp_off + i * 32);
+            if constexpr (PAIRS) {
 #pragma unroll
-            for (int i = 0; i < K; ++i) val[i] = ld_stream(in_val + tile_base + warp_off + i * 32);
+                for (int i = 0; i < K; ++i) val[i] = ld_stream(in_val + base + warp_off + i * 32);
+            }
+        } else {
+            const uint32_t v = static_cast<uint32_t>(n - base);
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t idx = warp_off + i * 32;
+                key[i] = idx < v ? in[base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));  // pad: ranks last
+                if constexpr (PAIRS) val[i] = idx < v ? in_val[base + idx] : 0u;
+            }
         }
-    } else {
+    };
+    auto zero_hist = [&]() {
+        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+        for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+    };
+
+    zero_hist();
+    if (tid == 0) {
+        sm.tile = atomicAdd(ticket, 1u);
+        if constexpr (PERSIST) sm.tile_next = atomicAdd(ticket, 1u);
+    }
+    __syncthreads();
+    uint32_t tile = sm.tile;
+    if (tile >= num_tiles) return;
+    load_tile(tile);
+
+    while (true) {
+        const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
+        const bool full = tile_base + T <= n;
+        const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
+
+        // ---- phase 1: count digits per warp (order-free, non-returning atomics) -----------------------
+#pragma unroll
+        for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift)], 1u);
+        __syncthreads();
+
+        // ---- per digit: tile reduction -> publish; scan over digits; per-warp slot bases ----------------
+        uint32_t tile_count = 0, tile_excl = 0;
+        if (tid < kRadix) {
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
+            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+        }
+        tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
+        if (tid < kRadix) {
+            uint32_t run = tile_excl;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
+        }
+        __syncthreads();
+
+        // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -------------
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const uint32_t idx = warp_off + i * 32;
-            key[i] = idx < valid ? in[tile_base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));  // pad: ranks last
-            if constexpr (PAIRS) val[i] = idx < valid ? in_val[tile_base + idx] : 0u;
+            const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
+            sm.sorted[slot] = key[i];
+            if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
         }
-    }
 
-    // ---- phase 1: count digits per warp (order-free, non-returning atomics) ---------------------------
-#pragma unroll
-    for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift)], 1u);
-    __syncthreads();
-
-    // ---- per digit: tile reduction -> publish; scan over digits; per-warp slot bases --------------------
-    uint32_t tile_count = 0, tile_excl = 0;
-    if (tid < kRadix) {
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
-        st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
-    }
-    tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
-    if (tid < kRadix) {
-        uint32_t run = tile_excl;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
-    }
-    __syncthreads();
-
-    // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -----------------
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
-        sm.sorted[slot] = key[i];
-        if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
-    }
-
-    // ---- chained scan with decoupled lookback ------------------------------------------------------------
-    if (tid < kRadix) {
-        const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch, gbase);
-        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
-                           desc_pack(epoch, kFlagInclusive, prior + tile_count));
-        const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
-        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
-        if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
-    }
-    __syncthreads();
-
-    // ---- scatter -----------------------------------------------------------------------------------------
-    if (full) {  // branch-free: all shared loads of the unrolled body can be in flight together
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const uint32_t idx = j * THREADS + tid;
-            const KeyT k = sm.sorted[idx];
-            const uint32_t d = digit_of(k, shift);
-            st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
-            if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
+        // ---- prefetch: the key registers are free again; start the next tile's loads now ------------------
+        uint32_t next = num_tiles;
+        if constexpr (PERSIST) {
+            next = sm.tile_next;  // written by thread 0 at least one barrier ago
+            if (next < num_tiles) load_tile(next);
         }
-    } else {
-#pragma unroll 4
-        for (int j = 0; j < K; ++j) {
-            const uint32_t idx = j * THREADS + tid;
-            if (idx < valid) {
+
+        // ---- chained scan with decoupled lookback --------------------------------------------------------
+        if (tid < kRadix) {
+            const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch, gbase);
+            st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
+                               desc_pack(epoch, kFlagInclusive, prior + tile_count));
+            const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
+            sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
+            if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
+        }
+        __syncthreads();
+
+        // ---- scatter -------------------------------------------------------------------------------------
+        if (full) {  // branch-free: all shared loads of the unrolled body can be in flight together
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const uint32_t idx = j * THREADS + tid;
                 const KeyT k = sm.sorted[idx];
                 const uint32_t d = digit_of(k, shift);
                 st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
                 if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
             }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < K; ++j) {
+                const uint32_t idx = j * THREADS + tid;
+                if (idx < valid) {
+                    const KeyT k = sm.sorted[idx];
+                    const uint32_t d = digit_of(k, shift);
+                    st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
+                    if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
+                }
+            }
         }
+        if constexpr (!PERSIST) return;
+        if (next >= num_tiles) return;
+        zero_hist();  // dead since the last barrier
+        if (tid == 0) sm.tile_next = atomicAdd(ticket, 1u);  // every thread read the old value before that barrier
+        __syncthreads();  // sorted tile drained, histograms cleared
+        tile = next;
     }
 }
 
@@ -808,17 +840,20 @@ template <> struct WideGeom<uint32_t, false, 0> { static constexpr int K = 32, W
 template <> struct WideGeom<uint32_t, true, 0>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
 template <> struct WideGeom<uint64_t, false, 0> { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
 
-template <typename KeyT, bool PAIRS, int RANK_MODE, int GEOM>
+template <typename KeyT, bool PAIRS, int RANK_MODE, int GEOM, bool PERSIST>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
                                        uint32_t shift, const unsigned long long* gbase, uint16_t* agg16, uint64_t* incl64,
-                                       uint32_t* ticket, uint32_t epoch, cudaStream_t stream)
+                                       uint32_t* ticket, uint32_t epoch, int sm_count, cudaStream_t stream)
 {
     using G = WideGeom<KeyT, PAIRS, GEOM>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
     const uint64_t tiles = (n + S::T - 1) / S::T;
-    auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>;
-    kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
-        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch);
+    uint64_t grid = tiles;
+    if (PERSIST && grid > static_cast<uint64_t>(sm_count) * G::MINB) grid = static_cast<uint64_t>(sm_count) * G::MINB;
+    auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, PERSIST>;
+    kern<<<static_cast<unsigned>(grid), S::THREADS, sizeof(S), stream>>>(
+        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch,
+        static_cast<uint32_t>(tiles));
     return cudaGetLastError();
 }
 
@@ -827,8 +862,13 @@ static cudaError_t set_wide_attr()
 {
     using G = WideGeom<KeyT, PAIRS, GEOM>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
-    return cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+    cudaError_t e = cudaFuncSetAttribute(
+        digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, false>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(
+        digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, true>,
+        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
 }
 
 // ---- variant-0 geometry ------------------------------------------------------------------------------
@@ -862,7 +902,7 @@ static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t
 
 uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
 {
-    if (cfg.variant == kVariantWide) {
+    if (cfg.variant == kVariantWide || cfg.variant == kVariantWidePersistent) {
         if (key_bytes == 8) return WideGeom<uint64_t, false, 0>::K * WideGeom<uint64_t, false, 0>::WARPS * 32;
         if (pairs) return WideGeom<uint32_t, true, 0>::K * WideGeom<uint32_t, true, 0>::WARPS * 32;
         return WideGeom<uint32_t, false, 0>::K * WideGeom<uint32_t, false, 0>::WARPS * 32;
@@ -914,16 +954,19 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
-    if (cfg.variant == kVariantWide) {
-#define OSB_WIDE(KEYT, PAIRS, GEOM)                                                                                       \
-    (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot, GEOM>(in, out, in_val, out_val, n, shift, gbase_place, agg16,   \
-                                                                 desc, ticket, epoch, stream)                              \
-            : launch_wide_variant<KEYT, PAIRS, kRankAtomic, GEOM>(in, out, in_val, out_val, n, shift, gbase_place, agg16,   \
-                                                                 desc, ticket, epoch, stream))
-        if (key_bytes == 4 && !pairs) return OSB_WIDE(uint32_t, false, 0);
-        if (key_bytes == 4) return OSB_WIDE(uint32_t, true, 0);
-        if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false, 0);
+    if (cfg.variant == kVariantWide || cfg.variant == kVariantWidePersistent) {
+        const bool persist = cfg.variant == kVariantWidePersistent;
+#define OSB_WIDE2(KEYT, PAIRS, RM)                                                                                          \
+    (persist ? launch_wide_variant<KEYT, PAIRS, RM, 0, true>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc,   \
+                                                            ticket, epoch, cfg.sm_count, stream)                            \
+             : launch_wide_variant<KEYT, PAIRS, RM, 0, false>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc,  \
+                                                             ticket, epoch, cfg.sm_count, stream))
+#define OSB_WIDE(KEYT, PAIRS) (ballot ? OSB_WIDE2(KEYT, PAIRS, kRankBallot) : OSB_WIDE2(KEYT, PAIRS, kRankAtomic))
+        if (key_bytes == 4 && !pairs) return OSB_WIDE(uint32_t, false);
+        if (key_bytes == 4) return OSB_WIDE(uint32_t, true);
+        if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false);
 #undef OSB_WIDE
+#undef OSB_WIDE2
         return cudaErrorInvalidValue;
     }
     if (cfg.variant == kVariantPersistent && !pairs) {

@@ -9,9 +9,10 @@ namespace osb {
 enum BinningVariant : int {
     kVariantTilePerCta = 0,  // one CTA per partition tile, keys loaded straight into registers
     kVariantPersistent = 1,  // persistent CTAs, TMA (cp.async.bulk) double-buffered tile staging
+    kVariantWidePersistent = 3,  // variant 2 with resident CTAs that prefetch their next tile's keys (register reuse)
     kVariantWide = 2,        // 16,384-key tiles, two-phase atomic ranking, compact reductions + one-shot lookback
 };
-constexpr int kNumVariants = 3;
+constexpr int kNumVariants = 4;
 enum RankMode : int {
     kRankAtomic = 0,  // one shared-memory atomicAdd per key (lane-ordered on sm_100, verified at create)
     kRankBallot = 1,  // 8 ballots per key (the reference's warp-level multisplit, OneSweep.cu:208-253)
