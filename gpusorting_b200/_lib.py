@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libonesweep_b200.so")
+LIB_PATH = os.environ.get("OSB200_LIB") or os.path.join(_HERE, "lib", "libonesweep_b200.so")  # override: build sweeps only
 
 c_u64, c_u32, c_i64, c_int, c_vp = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p
 
