@@ -432,7 +432,6 @@ int osb200_set_option(osb200_handle h, const char* key, int64_t value)
         return OSB200_OK;
     }
     if (!std::strcmp(key, "profile")) { h->profile = value != 0; return OSB200_OK; }
-    if (!std::strcmp(key, "wide_flags")) { osb::set_wide_flags(static_cast<uint32_t>(value)); return OSB200_OK; }  // tuning experiments
     if (!std::strcmp(key, "variant")) {
         if (value < 0 || value >= osb::kNumVariants) return OSB200_ERR_INVALID_ARG;
         h->cfg.variant = static_cast<int>(value);

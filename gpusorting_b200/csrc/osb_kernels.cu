@@ -635,8 +635,7 @@ __device__ __forceinline__ void st_relaxed_gpu_u16(uint16_t* p, uint32_t v)
 // below n even when the bases are peer addresses in the sharded exchange pass).
 template <int LOOK, int STEP>
 __device__ __forceinline__ unsigned long long
-lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d, uint32_t epoch,
-              const unsigned long long* __restrict__ /*gbase*/)
+lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d, uint32_t epoch)
 {
     static_assert(LOOK % STEP == 0, "probe spacing must divide the window");
     unsigned long long sum = 0;                       // reductions of tiles (cur, tile-1] already added
@@ -679,39 +678,23 @@ template <typename KeyT, bool PAIRS, int K, int WARPS>
 struct WideSmem {
     static constexpr int THREADS = WARPS * 32;
     static constexpr int T = THREADS * K;
-    static constexpr int E = 16 / sizeof(KeyT);           // elements per 16-byte vector
-    static constexpr int PAD = kRadix * 2 * (E - 1);      // aligned-run layout: <= E-1 slots of padding before and after each run
-    alignas(16) KeyT sorted[T + PAD];                     // digit-sorted tile
-    alignas(16) uint32_t sorted_val[PAIRS ? T + PAD : 4]; // payloads in the same order
-    alignas(16) uint32_t hist[WARPS * kRadix];  // warp-private digit counters (counts, then running slots)
-    unsigned long long keyptr[kRadix];          // per digit: byte address of out[first key of the digit - tile slot]
+    alignas(16) KeyT sorted[T];                      // digit-sorted tile
+    alignas(16) uint32_t sorted_val[PAIRS ? T : 4];  // payloads in the same order
+    alignas(16) uint32_t hist[WARPS * kRadix];       // warp-private digit counters (counts, then running slots)
+    unsigned long long keyptr[kRadix];               // per digit: byte address of out[first key of the digit - tile slot]
     unsigned long long valptr[PAIRS ? kRadix : 1];
-    uint32_t run[kRadix];                       // aligned-run layout: first slot (low 16 bits) and length (high 16) of every run
     uint32_t wtot[kRadix / 32];
     uint32_t tile;
-    uint32_t tile_next;
-    uint32_t slots;                             // aligned-run layout: slots in use (multiple of E)
 };
 
-// PERSIST = false: one CTA per partition tile.  PERSIST = true: a resident CTA loops over tiles it draws from the ticket
-// counter and issues the global loads of its NEXT tile right after the keys of the current one have been moved to shared
-// memory, so those loads (and the ticket round trip) overlap the lookback wait and the scatter; the key registers are
-// simply reused.  Tickets are drawn and consumed in increasing order by every CTA, so the lowest unfinished tile is
-// always being processed by a resident CTA (no deadlock).
-//
-// ALIGNED = true ("aligned runs"): the digit-sorted tile is laid out so that every run starts at a shared-memory slot
-// congruent (mod 16 bytes) to its GLOBAL destination.  The scatter then moves whole 16-byte vectors (LDS.128 / STG.128):
-// a quarter of the store instructions, one L1 tag per 128 bytes instead of ~2.5, no partial sectors inside a run.
-// The price is that the lookback has to finish before the rank phase (the slot bases depend on it) -- but the lookback
-// wait was exposed already (the non-digit warps idled behind it), it merely moves ahead of the rank phase.
-template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP, int MINB, bool PERSIST, bool ALIGNED>
+
+template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, const uint32_t* __restrict__ in_val,
                           uint32_t* __restrict__ out_val, uint64_t n, uint32_t shift,
                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
-                          uint32_t* ticket, uint32_t epoch, uint32_t num_tiles, uint32_t flags)
+                          uint32_t* ticket, uint32_t epoch)
 {
-    // flags (tuning experiments, default 0): bit 0 = write-back stores instead of streaming (evict-first) stores
     using S = WideSmem<KeyT, PAIRS, K, WARPS>;
     constexpr int THREADS = S::THREADS;
     constexpr int T = S::T;
@@ -722,281 +705,136 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
     uint32_t* wh = sm.hist + warp * kRadix;
-    const uint32_t warp_off = warp * (32 * K) + lane;
 
-    KeyT key[K];
-    uint32_t val[PAIRS ? K : 1];
-    // warp-striped loads: every warp instruction reads one contiguous 128 B / 256 B row
-    auto load_tile = [&](uint32_t t) {
-        const uint64_t base = static_cast<uint64_t>(t) * T;
-        if (base + T <= n) {
-#pragma unroll
-            for (int i = 0; i < K; ++i) key[i] = ld_stream(in + base + warp_off + i * 32);
-            if constexpr (PAIRS) {
-#pragma unroll
-                for (int i = 0; i < K; ++i) val[i] = ld_stream(in_val + base + warp_off + i * 32);
-            }
-        } else {
-            const uint32_t v = static_cast<uint32_t>(n - base);
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-                const uint32_t idx = warp_off + i * 32;
-                key[i] = idx < v ? in[base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));  // pad: ranks last
-                if constexpr (PAIRS) val[i] = idx < v ? in_val[base + idx] : 0u;
-            }
-        }
-    };
-    auto zero_hist = [&]() {
+    {
         uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
         for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
-    };
-
-    zero_hist();
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+    }
+    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);  // dynamic tile id: predecessors are already scheduled
     __syncthreads();
-    uint32_t tile = sm.tile;
-    if (tile >= num_tiles) return;
-    load_tile(tile);
+    const uint32_t tile = sm.tile;
+    const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
+    const bool full = tile_base + T <= n;
+    const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
 
-    while (true) {
-        const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
-        const bool full = tile_base + T <= n;
-        const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
-
-        // ---- phase 1: count digits per warp (order-free, non-returning atomics) -----------------------
+    // ---- load (warp-striped: every warp instruction reads one contiguous 128 B / 256 B row) ------------
+    KeyT key[K];
+    uint32_t val[PAIRS ? K : 1];
+    const uint32_t warp_off = warp * (32 * K) + lane;
+    if (full) {
 #pragma unroll
-        for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift)], 1u);
-        __syncthreads();
-
-        uint32_t next = num_tiles;
-        if constexpr (!ALIGNED) {
-        // ---- per digit: tile reduction -> publish; scan over digits; per-warp slot bases ----------------
-        uint32_t tile_count = 0, tile_excl = 0;
-        if (tid < kRadix) {
+        for (int i = 0; i < K; ++i) key[i] = ld_stream(in + tile_base + warp_off + i * 32);
+        if constexpr (PAIRS) {
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
-            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+            for (int i = 0; i < K; ++i) val[i] = ld_stream(in_val + tile_base + warp_off + i * 32);
         }
-        tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
-        if (tid < kRadix) {
-            uint32_t run = tile_excl;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
-        }
-        __syncthreads();
-
-        // The next ticket is drawn only now -- tickets must be drawn in the order tiles will publish their reductions,
-        // or successors of a tile that sits behind another tile of the same CTA would stall; its round trip overlaps
-        // the rank phase.
-        if constexpr (PERSIST) {
-            if (tid == 0) sm.tile_next = atomicAdd(ticket, 1u);
-        }
-
-        // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -------------
+    } else {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
-            const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
-            sm.sorted[slot] = key[i];
-            if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
+            const uint32_t idx = warp_off + i * 32;
+            key[i] = idx < valid ? in[tile_base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));  // pad: ranks last
+            if constexpr (PAIRS) val[i] = idx < valid ? in_val[tile_base + idx] : 0u;
         }
+    }
 
-        // ---- prefetch: the key registers are free again; start the next tile's loads now ------------------
-        if constexpr (PERSIST) {
-            __syncthreads();
-            next = sm.tile_next;
-            if (next < num_tiles) load_tile(next);
-        }
-
-        // ---- chained scan with decoupled lookback --------------------------------------------------------
-        if (tid < kRadix) {
-            const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch, gbase);
-            st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
-                               desc_pack(epoch, kFlagInclusive, prior + tile_count));
-            const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
-            sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
-            if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
-        }
-        __syncthreads();
-
-        // ---- scatter -------------------------------------------------------------------------------------
-        if (full && (flags & 1u)) {
+    // ---- phase 1: count digits per warp (order-free, non-returning atomics) ---------------------------
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                const uint32_t idx = j * THREADS + tid;
-                const KeyT k = sm.sorted[idx];
-                const uint32_t d = digit_of(k, shift);
-                reinterpret_cast<KeyT*>(sm.keyptr[d])[idx] = k;
-                if constexpr (PAIRS) reinterpret_cast<uint32_t*>(sm.valptr[d])[idx] = sm.sorted_val[idx];
-            }
-        } else if (full) {  // branch-free: all shared loads of the unrolled body can be in flight together
+    for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift)], 1u);
+    __syncthreads();
+
+    // ---- per digit: tile reduction -> publish; scan over digits; per-warp slot bases --------------------
+    uint32_t tile_count = 0, tile_excl = 0;
+    if (tid < kRadix) {
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                const uint32_t idx = j * THREADS + tid;
+        for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
+        st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+    }
+    tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
+    if (tid < kRadix) {
+        uint32_t run = tile_excl;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
+    }
+    __syncthreads();
+
+    // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -----------------
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
+        sm.sorted[slot] = key[i];
+        if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
+    }
+
+    // ---- chained scan with decoupled lookback ------------------------------------------------------------
+    if (tid < kRadix) {
+        const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch);
+        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
+                           desc_pack(epoch, kFlagInclusive, prior + tile_count));
+        const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
+        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
+        if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
+    }
+    __syncthreads();
+
+    // ---- scatter -----------------------------------------------------------------------------------------
+    if (full) {  // branch-free: all shared loads of the unrolled body can be in flight together
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            const KeyT k = sm.sorted[idx];
+            const uint32_t d = digit_of(k, shift);
+            st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
+            if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            if (idx < valid) {
                 const KeyT k = sm.sorted[idx];
                 const uint32_t d = digit_of(k, shift);
                 st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
                 if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
             }
-        } else {
-#pragma unroll 4
-            for (int j = 0; j < K; ++j) {
-                const uint32_t idx = j * THREADS + tid;
-                if (idx < valid) {
-                    const KeyT k = sm.sorted[idx];
-                    const uint32_t d = digit_of(k, shift);
-                    st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
-                    if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
-                }
-            }
         }
-        } else {
-        // =========================== aligned-run layout ==================================================
-        constexpr uint32_t E = S::E;
-        // ---- per digit: tile reduction -> publish; region sizes; lookback; slot bases -----------------------
-        uint32_t tile_count = 0, region = 0;
-        if (tid < kRadix) {
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
-            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
-            region = (tile_count + 2 * (E - 1)) & ~(E - 1);  // room for <= E-1 slots of padding on either side
-        }
-        const uint32_t region_base = block_excl_scan_256<THREADS>(region, sm.wtot);  // multiple of E
-        if (tid < kRadix) {
-            const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch, gbase);
-            st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
-                               desc_pack(epoch, kFlagInclusive, prior + tile_count));
-            const unsigned long long g = gbase[tid] + prior;          // global element index of the run's first key
-            const uint32_t s0 = region_base + (static_cast<uint32_t>(g) & (E - 1));  // same 16-byte phase as its destination
-            // keys past `valid` are the all-ones padding of the ragged last tile: they sit at the end of run 255
-            const uint32_t live = tile_count - ((tid == kRadix - 1 && !full) ? (T - valid) : 0u);
-            sm.run[tid] = s0 | (live << 16);
-            sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + (g - s0) * sizeof(KeyT);
-            if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + (g - s0) * sizeof(uint32_t);
-            uint32_t run = s0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
-            if (tid == kRadix - 1) sm.slots = region_base + region;
-        }
-        __syncthreads();
-        if constexpr (PERSIST) {
-            if (tid == 0) sm.tile_next = atomicAdd(ticket, 1u);
-        }
-
-        // ---- rank: the returning atomic hands every key its slot ------------------------------------------
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
-            sm.sorted[slot] = key[i];
-            if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
-        }
-        __syncthreads();
-        if constexpr (PERSIST) {
-            next = sm.tile_next;
-            if (next < num_tiles) load_tile(next);
-        }
-
-        // ---- scatter ---------------------------------------------------------------------------------------------
-        // (a) the <= E-1 keys before the first and after the last 16-byte boundary of every run: its digit thread, scalar
-        if (tid < kRadix) {
-            const uint32_t rd = sm.run[tid];
-            const uint32_t lo = rd & 0xffffu, hi = lo + (rd >> 16);
-            uint32_t head_end = (lo + E - 1) & ~(E - 1);
-            if (head_end > hi) head_end = hi;
-            uint32_t tail_start = hi & ~(E - 1);
-            if (tail_start < head_end) tail_start = head_end;
-            KeyT* kdst = reinterpret_cast<KeyT*>(sm.keyptr[tid]);
-            for (uint32_t x = lo; x < head_end; ++x) {
-                st_stream(kdst + x, sm.sorted[x]);
-                if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[tid]) + x, sm.sorted_val[x]);
-            }
-            for (uint32_t x = tail_start; x < hi; ++x) {
-                st_stream(kdst + x, sm.sorted[x]);
-                if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[tid]) + x, sm.sorted_val[x]);
-            }
-        }
-        // (b) every 16-byte vector that lies completely inside a run: one LDS.128 + STG.128 per thread and step.  A vector
-        // that is not inside a run (padding, or a run boundary handled above) fails the range test whatever stale data its
-        // first slot holds: the range of the digit it decodes to is disjoint from the vector or does not cover it.
-        using Vec = uint4;
-        const uint32_t groups = sm.slots / E;
-        constexpr int JMAX = (S::T + S::PAD) / static_cast<int>(E) / THREADS + 1;
-#pragma unroll
-        for (int j = 0; j < JMAX; ++j) {
-            const uint32_t q = j * THREADS + tid;
-            if (q < groups) {
-                const uint32_t x0 = q * E;
-                const Vec kv = *reinterpret_cast<const Vec*>(&sm.sorted[x0]);
-                KeyT k0;
-                if constexpr (E == 4) k0 = kv.x; else k0 = (static_cast<KeyT>(kv.y) << 32) | kv.x;
-                const uint32_t d = digit_of(k0, shift);
-                const uint32_t rd = sm.run[d];
-                const uint32_t lo = rd & 0xffffu, hi = lo + (rd >> 16);
-                if (x0 >= lo && x0 + E <= hi) {
-                    __stcs(reinterpret_cast<Vec*>(reinterpret_cast<KeyT*>(sm.keyptr[d]) + x0), kv);
-                    if constexpr (PAIRS) {
-                        const Vec vv = *reinterpret_cast<const Vec*>(&sm.sorted_val[x0]);
-                        __stcs(reinterpret_cast<Vec*>(reinterpret_cast<uint32_t*>(sm.valptr[d]) + x0), vv);
-                    }
-                }
-            }
-        }
-        }
-        if constexpr (!PERSIST) return;
-        if (next >= num_tiles) return;
-        zero_hist();  // dead since the last barrier
-        __syncthreads();  // sorted tile drained, histograms cleared
-        tile = next;
     }
 }
 
-// Geometry.  Measured alternatives (n = 2^30 u32 keys, ms per pass; profiles/r01_geometry_experiments.txt):
-//   16,384-key tiles, 2 x 512 threads per SM (this one) 2.80 | 8,192-key tiles, 3 CTAs/SM 5.46 (lookback window doubles,
-//   spills) | 31,744-key tiles, 1 x 1024 threads per SM 3.15 (no second CTA to overlap barriers and the lookback wait).
-template <typename KeyT, bool PAIRS, int GEOM> struct WideGeom;
-#ifndef OSB_LOOK  // overridable for parameter sweeps (tools/sweep.sh); the committed values are the measured best
-#define OSB_LOOK 16
-#define OSB_STEP 8
+// Geometry and lookback window.  Measured alternatives at n = 2^30 u32 keys (profiles/r01_geometry_experiments.txt,
+// profiles/r01_wide_kernel_experiments.txt), ms per pass: 16,384-key tiles on 2 x 512 threads per SM (this one) 2.80;
+// 8,192-key tiles, 3 CTAs/SM 5.46; 31,744-key tiles on 1 x 1024 threads 3.15; resident CTAs prefetching their next
+// tile's keys 3.08; run layout aligned for 16-byte vector stores 3.25.  Lookback window/probe spacing (whole sort, ms):
+// 8/4 11.71, 8/8 11.77, 16/4 11.89, 16/8 11.97, 24/8 12.06, 16/16 12.20, 32/8 12.99.
+#ifndef OSB_LOOK  // overridable for parameter sweeps (tools/sweep.sh)
+#define OSB_LOOK 8
+#define OSB_STEP 4
 #endif
-template <> struct WideGeom<uint32_t, false, 0> { static constexpr int K = 32, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
-template <> struct WideGeom<uint32_t, true, 0>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
-template <> struct WideGeom<uint64_t, false, 0> { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = 16, STEP = 8; };
+template <typename KeyT, bool PAIRS> struct WideGeom;
+template <> struct WideGeom<uint32_t, false> { static constexpr int K = 32, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
+template <> struct WideGeom<uint32_t, true>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
+template <> struct WideGeom<uint64_t, false> { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
 
-static uint32_t g_wide_flags = 0;  // tuning experiments, see digit_binning_wide_kernel
-void set_wide_flags(uint32_t v) { g_wide_flags = v; }
-
-template <typename KeyT, bool PAIRS, int RANK_MODE, int GEOM, bool PERSIST, bool ALIGNED>
+template <typename KeyT, bool PAIRS, int RANK_MODE>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
                                        uint32_t shift, const unsigned long long* gbase, uint16_t* agg16, uint64_t* incl64,
-                                       uint32_t* ticket, uint32_t epoch, int sm_count, cudaStream_t stream)
+                                       uint32_t* ticket, uint32_t epoch, cudaStream_t stream)
 {
-    using G = WideGeom<KeyT, PAIRS, GEOM>;
+    using G = WideGeom<KeyT, PAIRS>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
     const uint64_t tiles = (n + S::T - 1) / S::T;
-    uint64_t grid = tiles;
-    if (PERSIST && grid > static_cast<uint64_t>(sm_count) * G::MINB) grid = static_cast<uint64_t>(sm_count) * G::MINB;
-    auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, PERSIST, ALIGNED>;
-    kern<<<static_cast<unsigned>(grid), S::THREADS, sizeof(S), stream>>>(
-        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch,
-        static_cast<uint32_t>(tiles), g_wide_flags);
+    auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>;
+    kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
+        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch);
     return cudaGetLastError();
 }
 
-template <typename KeyT, bool PAIRS, int RANK_MODE, int GEOM>
+template <typename KeyT, bool PAIRS, int RANK_MODE>
 static cudaError_t set_wide_attr()
 {
-    using G = WideGeom<KeyT, PAIRS, GEOM>;
+    using G = WideGeom<KeyT, PAIRS>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
-    cudaError_t e = cudaFuncSetAttribute(
-        digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, false, false>,
-        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(
-        digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, false, true>,
-        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(
-        digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, true, false>,
-        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+    return cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
 }
 
 // ---- variant-0 geometry ------------------------------------------------------------------------------
@@ -1030,10 +868,10 @@ static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t
 
 uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
 {
-    if (cfg.variant >= kVariantWide) {
-        if (key_bytes == 8) return WideGeom<uint64_t, false, 0>::K * WideGeom<uint64_t, false, 0>::WARPS * 32;
-        if (pairs) return WideGeom<uint32_t, true, 0>::K * WideGeom<uint32_t, true, 0>::WARPS * 32;
-        return WideGeom<uint32_t, false, 0>::K * WideGeom<uint32_t, false, 0>::WARPS * 32;
+    if (cfg.variant == kVariantWide) {
+        if (key_bytes == 8) return WideGeom<uint64_t, false>::K * WideGeom<uint64_t, false>::WARPS * 32;
+        return pairs ? WideGeom<uint32_t, true>::K * WideGeom<uint32_t, true>::WARPS * 32
+                     : WideGeom<uint32_t, false>::K * WideGeom<uint32_t, false>::WARPS * 32;
     }
     if (key_bytes == 8) return TileGeom<uint64_t, false>::WARPS * 32 * TileGeom<uint64_t, false>::K;
     if (pairs) return TileGeom<uint32_t, true>::WARPS * 32 * TileGeom<uint32_t, true>::K;
@@ -1066,12 +904,12 @@ cudaError_t configure_kernels()
     if ((e = set_persistent_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_persistent_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_persistent_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, false, kRankAtomic, 0>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, false, kRankBallot, 0>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, true, kRankAtomic, 0>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint32_t, true, kRankBallot, 0>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint64_t, false, kRankAtomic, 0>()) != cudaSuccess) return e;
-    if ((e = set_wide_attr<uint64_t, false, kRankBallot, 0>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, false, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, true, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint32_t, true, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint64_t, false, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_wide_attr<uint64_t, false, kRankBallot>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1082,22 +920,15 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
-    if (cfg.variant == kVariantWide || cfg.variant == kVariantWidePersistent || cfg.variant == kVariantWideAligned) {
-#define OSB_WIDE2(KEYT, PAIRS, RM)                                                                                          \
-    (cfg.variant == kVariantWidePersistent                                                                                  \
-         ? launch_wide_variant<KEYT, PAIRS, RM, 0, true, false>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
-                                                                ticket, epoch, cfg.sm_count, stream)                        \
-     : cfg.variant == kVariantWideAligned                                                                                   \
-         ? launch_wide_variant<KEYT, PAIRS, RM, 0, false, true>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
-                                                                ticket, epoch, cfg.sm_count, stream)                        \
-         : launch_wide_variant<KEYT, PAIRS, RM, 0, false, false>(in, out, in_val, out_val, n, shift, gbase_place, agg16,    \
-                                                                 desc, ticket, epoch, cfg.sm_count, stream))
-#define OSB_WIDE(KEYT, PAIRS) (ballot ? OSB_WIDE2(KEYT, PAIRS, kRankBallot) : OSB_WIDE2(KEYT, PAIRS, kRankAtomic))
-        if (key_bytes == 4 && !pairs) return OSB_WIDE(uint32_t, false);
-        if (key_bytes == 4) return OSB_WIDE(uint32_t, true);
+    if (cfg.variant == kVariantWide) {
+#define OSB_WIDE(KEYT, PAIRS)                                                                                          \
+    (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
+                                                           ticket, epoch, stream)                                      \
+            : launch_wide_variant<KEYT, PAIRS, kRankAtomic>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
+                                                           ticket, epoch, stream))
+        if (key_bytes == 4) return pairs ? OSB_WIDE(uint32_t, true) : OSB_WIDE(uint32_t, false);
         if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false);
 #undef OSB_WIDE
-#undef OSB_WIDE2
         return cudaErrorInvalidValue;
     }
     if (cfg.variant == kVariantPersistent && !pairs) {

@@ -9,11 +9,9 @@ namespace osb {
 enum BinningVariant : int {
     kVariantTilePerCta = 0,  // one CTA per partition tile, keys loaded straight into registers
     kVariantPersistent = 1,  // persistent CTAs, TMA (cp.async.bulk) double-buffered tile staging
-    kVariantWidePersistent = 3,  // variant 2 with resident CTAs that prefetch their next tile's keys (register reuse)
-    kVariantWideAligned = 4,  // variant 2 with the aligned-run tile layout: 16-byte vector scatter
     kVariantWide = 2,        // 16,384-key tiles, two-phase atomic ranking, compact reductions + one-shot lookback
 };
-constexpr int kNumVariants = 5;
+constexpr int kNumVariants = 3;
 enum RankMode : int {
     kRankAtomic = 0,  // one shared-memory atomicAdd per key (lane-ordered on sm_100, verified at create)
     kRankBallot = 1,  // 8 ballots per key (the reference's warp-level multisplit, OneSweep.cu:208-253)
@@ -63,9 +61,6 @@ cudaError_t launch_validate(const void* keys, uint64_t n, int key_bytes, unsigne
 // payload (may be null) receives a copy of the key (reference pairs overload) or, if payload_is_index, i.
 cudaError_t launch_init_random(uint32_t* keys, uint32_t* payload, uint64_t n, uint32_t and_count, uint32_t seed,
                                bool payload_is_index, cudaStream_t stream);
-
-// Tuning experiments on the wide kernel (0 = default behaviour).
-void set_wide_flags(uint32_t v);
 
 // Device self-test: does a shared-memory atomicAdd hand out its return values in ascending lane order among
 // the lanes of one warp instruction that hit the same address?  (kRankAtomic depends on it.)

@@ -52,7 +52,7 @@ def test_init_random_matches_oracle(g, oracle):
         assert np.array_equal(host_u32(t), oracle.init_random_u32(n, andc, seed))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_keys_u32_edge_sizes(sorter, oracle, mode, variant):
     sorter.set_option("rank_mode", mode)
@@ -71,7 +71,7 @@ def test_keys_u32_edge_sizes(sorter, oracle, mode, variant):
         sorter.set_option("variant", DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_reference_size_sweep(sorter, oracle, variant):
     """The reference's TestAllKeysOnly sweep shape (OneSweepDispatcher.cuh:98-113): sizes across one..two of ITS
     tiles (7680..15360) and across one..two of OUR tiles, seed = n, checked bit-exactly (the reference only
@@ -90,7 +90,7 @@ def test_reference_size_sweep(sorter, oracle, variant):
         sorter.set_option("variant", DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("andc", [0, 1, 2, 3, 4])
 def test_entropy_presets_2pow22(sorter, oracle, andc, variant):
     n = 1 << 22
@@ -105,7 +105,7 @@ def test_entropy_presets_2pow22(sorter, oracle, andc, variant):
         sorter.set_option("variant", DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("variant", [2, 4])
+@pytest.mark.parametrize("variant", [1, 2])
 def test_adversarial_distributions(sorter, oracle, variant):
     sorter.set_option("variant", variant)
     n = 300001
@@ -129,7 +129,7 @@ def test_adversarial_distributions(sorter, oracle, variant):
         sorter.set_option("variant", DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("variant", [0, 2, 4])
+@pytest.mark.parametrize("variant", [0, 2])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_pairs_are_stable_payload_is_index(sorter, oracle, mode, variant):
     sorter.set_option("rank_mode", mode)
@@ -148,7 +148,7 @@ def test_pairs_are_stable_payload_is_index(sorter, oracle, mode, variant):
         sorter.set_option("variant", DEFAULT_VARIANT)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_keys_u64(g, oracle, variant):
     s = g.OneSweepSorter(1 << 21, 8, 0)
     s.set_option("variant", variant)

@@ -42,7 +42,6 @@ def main():
         hist_ms, _ = time_ms(lambda: s.global_histogram(src))
         print(f"n=2^{e} global_histogram(+memset) {hist_ms:.3f} ms ({4*n/hist_ms/1e6:.0f} GB/s read)", flush=True)
         dst = torch.empty_like(src)
-        s.set_option("wide_flags", int(os.environ.get("OSB_WIDE_FLAGS", "0")))
         for variant in VARIANTS:
             s.set_option("variant", variant)
             for mode in MODES:
