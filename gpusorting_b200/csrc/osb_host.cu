@@ -118,7 +118,7 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
     const int places = s->key_bytes;
 
     OSB_TRY(cudaMemsetAsync(s->control, 0, ControlLayout::zeroed_bytes, stream));
-    const bool wide = s->cfg.variant >= osb::kVariantWide;
+    const bool wide = s->cfg.variant != osb::kVariantTilePerCta;  // every other variant uses the compact reductions
     const uint64_t agg_stride = tiles_for(n, osb::binning_tile_keys(s->key_bytes, d_vals != nullptr, s->cfg)) * osb::kRadix;
     if (wide) OSB_TRY(cudaMemsetAsync(s->agg16, 0, agg_stride * places * sizeof(uint16_t), stream));
     int ne = 0;
@@ -206,7 +206,7 @@ int osb_internal_binning_pass(osb200_handle h, const void* d_in, void* d_out, ui
         OSB_TRY(osb::launch_scan(d_hist256, h->gbase(), 1, stream));
         base = h->gbase();
     }
-    if (h->cfg.variant >= osb::kVariantWide) {
+    if (h->cfg.variant != osb::kVariantTilePerCta) {
         const uint64_t tiles = tiles_for(n, osb::binning_tile_keys(h->key_bytes, false, h->cfg));
         OSB_TRY(cudaMemsetAsync(h->agg16, 0, tiles * osb::kRadix * sizeof(uint16_t), stream));
     }
@@ -388,7 +388,7 @@ int osb200_digit_binning_pass(osb200_handle h, const void* d_in, void* d_out, co
     uint32_t epoch = 0;
     int st = next_epoch(h, q, &epoch);
     if (st != OSB200_OK) return st;
-    if (h->cfg.variant >= osb::kVariantWide)
+    if (h->cfg.variant != osb::kVariantTilePerCta)
         OSB_TRY(cudaMemsetAsync(h->agg16, 0, h->desc_tiles * osb::kRadix * sizeof(uint16_t), q));
     OSB_TRY(osb::launch_digit_binning(d_in, d_out, d_in_values, d_out_values, n, h->key_bytes, radix_shift,
                                       h->gbase() + place * osb::kRadix, h->desc, h->agg16, h->tickets() + place, epoch,
@@ -455,7 +455,7 @@ int64_t osb200_get_info(osb200_handle h, const char* key)
     if (check_handle(h) != OSB200_OK || !key) return OSB200_ERR_INVALID_ARG;
     if (!std::strcmp(key, "tile_keys")) return osb::binning_tile_keys(h->key_bytes, h->value_bytes != 0, h->cfg);
     if (!std::strcmp(key, "launches_per_sort")) return 2 + h->key_bytes;  // histogram + scan + one pass per place
-    if (!std::strcmp(key, "memsets_per_sort")) return h->cfg.variant >= osb::kVariantWide ? 2 : 1;
+    if (!std::strcmp(key, "memsets_per_sort")) return h->cfg.variant != osb::kVariantTilePerCta ? 2 : 1;
     if (!std::strcmp(key, "sm_count")) return h->sm_count;
     if (!std::strcmp(key, "rank_mode")) return h->cfg.rank_mode;
     if (!std::strcmp(key, "variant")) return h->cfg.variant;

@@ -404,12 +404,7 @@ digit_binning_tile_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
 }
 
 // =====================================================================================================
-// DigitBinningPass, variant 1: persistent CTAs, partition tiles staged by TMA bulk copies (cp.async.bulk,
-// SASS UBLKCP) into a two-deep shared-memory ring.  While a CTA ranks and scatters tile p, the keys of its
-// next tile are already in flight, so neither the tile-ticket round trip nor the HBM load latency is on the
-// per-tile critical path.  Tickets are still handed out in increasing order and each CTA consumes its
-// tickets in order, so the lowest unfinished tile is always being processed by a resident CTA: the chained
-// scan cannot deadlock (same argument as the reference's dynamic partition index, OneSweep.cu:181-184).
+// TMA / mbarrier helpers used by DigitBinningPass variant 1 (the persistent, TMA-staged ring kernel further down).
 // =====================================================================================================
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -441,162 +436,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-template <typename KeyT, int K, int WARPS>
-struct PersistSmem {
-    static constexpr int THREADS = WARPS * 32;
-    static constexpr int T = THREADS * K;
-    alignas(128) KeyT stage[2][T];       // TMA destination; after ranking, the digit-sorted tile of the same slot
-    uint32_t hist[WARPS * kRadix];       // warp-private digit histograms
-    unsigned long long keyptr[kRadix];   // per digit: byte address of out[global_base - tile_base]
-    alignas(8) uint64_t bar[2];          // "stage filled" mbarriers
-    uint32_t tile[2];                    // ticket held in each stage
-    uint32_t wtot[kRadix / 32];
-};
-
-template <typename KeyT, int K, int WARPS, int RANK_MODE>
-__global__ void __launch_bounds__(WARPS * 32, 2)
-digit_binning_persistent_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, uint64_t n, uint32_t shift,
-                                const unsigned long long* __restrict__ gbase, uint64_t* desc, uint32_t* ticket,
-                                uint32_t epoch, uint32_t num_tiles)
-{
-    using S = PersistSmem<KeyT, K, WARPS>;
-    constexpr int THREADS = S::THREADS;
-    constexpr int T = S::T;
-    constexpr uint32_t TILE_BYTES = T * sizeof(KeyT);
-    extern __shared__ __align__(128) unsigned char s_raw[];
-    S& sm = *reinterpret_cast<S*>(s_raw);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt = lanemask_lt();
-    uint32_t* wh = sm.hist + warp * kRadix;
-    const uint32_t warp_off = warp * (32 * K) + lane;
-
-    // a stage is filled by TMA only for full tiles; the (single) ragged last tile is read with guarded loads
-    auto fetch = [&](int slot) {  // thread 0 only
-        const uint32_t t = atomicAdd(ticket, 1u);
-        sm.tile[slot] = t;
-        if (t < num_tiles && static_cast<uint64_t>(t + 1) * T <= n) {
-            mbar_expect_tx(&sm.bar[slot], TILE_BYTES);
-            tma_load_1d(sm.stage[slot], in + static_cast<uint64_t>(t) * T, TILE_BYTES, &sm.bar[slot]);
-        }
-    };
-
-    for (int i = tid; i < WARPS * kRadix; i += THREADS) sm.hist[i] = 0;
-    if (tid == 0) {
-        mbar_init(&sm.bar[0], 1);
-        mbar_init(&sm.bar[1], 1);
-        fence_mbar_init();
-        fetch(0);
-        fetch(1);
-    }
-    __syncthreads();
-
-    for (uint32_t it = 0;; ++it) {
-        const int slot = it & 1;
-        const uint32_t tile = sm.tile[slot];
-        if (tile >= num_tiles) break;  // tickets only grow: nothing left for this CTA
-        const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
-        const bool full = tile_base + T <= n;
-        const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
-        KeyT* s_keys = sm.stage[slot];
-
-        // ---- keys: shared (TMA-filled) -> registers, warp-striped so every LDS row is conflict-free ------
-        KeyT key[K];
-        if (full) {
-            mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
-#pragma unroll
-            for (int i = 0; i < K; ++i) key[i] = s_keys[warp_off + i * 32];
-        } else {
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-                const uint32_t idx = warp_off + i * 32;
-                key[i] = idx < valid ? in[tile_base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));
-            }
-        }
-
-        // ---- rank -------------------------------------------------------------------------------------
-        uint32_t off[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) off[i] = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
-        __syncthreads();  // (A) histograms complete; every key of the stage is in registers
-
-        // ---- per digit: prefix over warps, tile reduction, publish, scan over digits --------------------
-        uint32_t tile_count = 0, tile_excl = 0;
-        {
-            if (tid < kRadix) {
-#pragma unroll
-                for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
-                st_relaxed_gpu_u64(desc + static_cast<uint64_t>(tile) * kRadix + tid,
-                                   desc_pack(epoch, kFlagReduction, tile_count));
-            }
-            tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);  // (B) inside
-            if (tid < kRadix) {
-                uint32_t run = tile_excl;
-#pragma unroll
-                for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
-            }
-        }
-        __syncthreads();  // (C)
-
-        // ---- transpose: the stage now receives the digit-sorted tile --------------------------------------
-#pragma unroll
-        for (int i = 0; i < K; ++i) s_keys[off[i] + wh[digit_of(key[i], shift)]] = key[i];
-
-        // ---- chained scan with decoupled lookback --------------------------------------------------------
-        if (tid < kRadix) {
-            const unsigned long long excl = lookback_and_publish(desc, tile, tid, tile_count, epoch, gbase);
-            sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + (excl - tile_excl) * sizeof(KeyT);
-        }
-        __syncthreads();  // (D) sorted tile + digit pointers ready; histograms dead
-
-        // ---- scatter -------------------------------------------------------------------------------------
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const uint32_t idx = j * THREADS + tid;
-            if (idx < valid) {
-                const KeyT k = s_keys[idx];
-                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[digit_of(k, shift)]) + idx, k);
-            }
-        }
-        for (int i = tid; i < WARPS * kRadix; i += THREADS) sm.hist[i] = 0;
-        __syncthreads();  // (E) stage drained, histograms cleared
-        if (tid == 0) {
-            fence_proxy_async_smem();  // generic-proxy accesses of the stage happen-before the next TMA write
-            fetch(slot);
-        }
-        // the other stage's ticket was written at least one iteration (and one barrier) ago
-    }
-}
-
-template <typename KeyT> struct PersistGeom;
-template <> struct PersistGeom<uint32_t> { static constexpr int K = 16, WARPS = 16; };
-template <> struct PersistGeom<uint64_t> { static constexpr int K = 8,  WARPS = 16; };
-
-template <typename KeyT, int RANK_MODE>
-static cudaError_t launch_persistent_variant(const void* in, void* out, uint64_t n, uint32_t shift,
-                                             const unsigned long long* gbase, uint64_t* desc, uint32_t* ticket,
-                                             uint32_t epoch, int sm_count, cudaStream_t stream)
-{
-    using G = PersistGeom<KeyT>;
-    using S = PersistSmem<KeyT, G::K, G::WARPS>;
-    const uint64_t tiles = (n + S::T - 1) / S::T;
-    const uint64_t cap = static_cast<uint64_t>(sm_count) * 2;
-    const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
-    auto kern = digit_binning_persistent_kernel<KeyT, G::K, G::WARPS, RANK_MODE>;
-    kern<<<grid, S::THREADS, sizeof(S), stream>>>(static_cast<const KeyT*>(in), static_cast<KeyT*>(out), n, shift, gbase,
-                                                   desc, ticket, epoch, static_cast<uint32_t>(tiles));
-    return cudaGetLastError();
-}
-
-template <typename KeyT, int RANK_MODE>
-static cudaError_t set_persistent_attr()
-{
-    using G = PersistGeom<KeyT>;
-    using S = PersistSmem<KeyT, G::K, G::WARPS>;
-    return cudaFuncSetAttribute(digit_binning_persistent_kernel<KeyT, G::K, G::WARPS, RANK_MODE>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
-}
 
 // =====================================================================================================
 // DigitBinningPass, variant 2 ("wide tile"): 16,384-key partition tiles, two CTAs per SM.
@@ -800,6 +639,181 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     }
 }
 
+// =====================================================================================================
+// DigitBinningPass, variant 1 ("ring"): persistent CTAs, partition tiles staged by TMA bulk copies (cp.async.bulk,
+// SASS UBLKCP) into a two-deep shared-memory ring, with the wide kernel's ranking (two atomics per key), compact
+// reductions and windowed lookback.  While a CTA ranks and scatters tile p, the keys of its next tile are already
+// in flight (a full tile per CTA, all the time), so neither the ticket round trip nor the HBM load latency is on the
+// per-tile critical path and the memory system sees a steady stream instead of one burst per CTA lifetime.  The ring
+// costs shared memory: 8,192-key tiles (2 x 32 KB stages + 16 KB histograms, two CTAs per SM).
+// Every CTA draws a ticket when a stage becomes free and consumes its tickets in order, so the lowest unfinished tile
+// is always being processed by a resident CTA: the chained scan cannot deadlock (OneSweep.cu:181-184 argument).
+// =====================================================================================================
+template <typename KeyT, int K, int WARPS>
+struct RingSmem {
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int T = THREADS * K;
+    alignas(128) KeyT stage[2][T];              // TMA destination; after ranking, the digit-sorted tile of the same slot
+    alignas(16) uint32_t hist[WARPS * kRadix];  // warp-private digit counters
+    unsigned long long keyptr[kRadix];
+    alignas(8) uint64_t bar[2];                 // "stage filled" mbarriers
+    uint32_t tile[2];                           // ticket held in each stage
+    uint32_t wtot[kRadix / 32];
+};
+
+template <typename KeyT, int K, int WARPS, int RANK_MODE, int LOOK, int STEP>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+digit_binning_ring_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, uint64_t n, uint32_t shift,
+                          const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
+                          uint32_t* ticket, uint32_t epoch, uint32_t num_tiles)
+{
+    using S = RingSmem<KeyT, K, WARPS>;
+    constexpr int THREADS = S::THREADS;
+    constexpr int T = S::T;
+    constexpr uint32_t TILE_BYTES = T * sizeof(KeyT);
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    S& sm = *reinterpret_cast<S*>(s_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    uint32_t* wh = sm.hist + warp * kRadix;
+    const uint32_t warp_off = warp * (32 * K) + lane;
+
+    // a stage is filled by TMA only for full tiles; the (single) ragged last tile is read with guarded loads
+    auto fetch = [&](int slot) {  // thread 0 only
+        const uint32_t t = atomicAdd(ticket, 1u);
+        sm.tile[slot] = t;
+        if (t < num_tiles && static_cast<uint64_t>(t + 1) * T <= n) {
+            mbar_expect_tx(&sm.bar[slot], TILE_BYTES);
+            tma_load_1d(sm.stage[slot], in + static_cast<uint64_t>(t) * T, TILE_BYTES, &sm.bar[slot]);
+        }
+    };
+    auto zero_hist = [&]() {
+        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+        for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+    };
+
+    zero_hist();
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        fence_mbar_init();
+        fetch(0);
+        fetch(1);
+    }
+    __syncthreads();
+
+    for (uint32_t it = 0;; ++it) {
+        const int slot = it & 1;
+        const uint32_t tile = sm.tile[slot];
+        if (tile >= num_tiles) break;  // tickets only grow: nothing left for this CTA
+        const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
+        const bool full = tile_base + T <= n;
+        const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
+        KeyT* s_keys = sm.stage[slot];
+
+        // ---- keys: shared (TMA-filled) -> registers, warp-striped so every LDS row is conflict-free ------
+        KeyT key[K];
+        if (full) {
+            mbar_wait(&sm.bar[slot], (it >> 1) & 1u);
+#pragma unroll
+            for (int i = 0; i < K; ++i) key[i] = s_keys[warp_off + i * 32];
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t idx = warp_off + i * 32;
+                key[i] = idx < valid ? in[tile_base + idx] : static_cast<KeyT>(~static_cast<KeyT>(0));
+            }
+        }
+
+        // ---- phase 1: count ----------------------------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift)], 1u);
+        __syncthreads();  // counts complete; every key of the stage is in registers
+
+        uint32_t tile_count = 0, tile_excl = 0;
+        if (tid < kRadix) {
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
+            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+        }
+        tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
+        if (tid < kRadix) {
+            uint32_t run = tile_excl;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
+        }
+        __syncthreads();
+
+        // ---- phase 2: rank; the stage now receives the digit-sorted tile --------------------------------
+#pragma unroll
+        for (int i = 0; i < K; ++i) s_keys[warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt)] = key[i];
+
+        if (tid < kRadix) {
+            const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch);
+            st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
+                               desc_pack(epoch, kFlagInclusive, prior + tile_count));
+            sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + (gbase[tid] + prior - tile_excl) * sizeof(KeyT);
+        }
+        __syncthreads();
+
+        // ---- scatter -----------------------------------------------------------------------------------
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const uint32_t idx = j * THREADS + tid;
+                const KeyT k = s_keys[idx];
+                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[digit_of(k, shift)]) + idx, k);
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < K; ++j) {
+                const uint32_t idx = j * THREADS + tid;
+                if (idx < valid) {
+                    const KeyT k = s_keys[idx];
+                    st_stream(reinterpret_cast<KeyT*>(sm.keyptr[digit_of(k, shift)]) + idx, k);
+                }
+            }
+        }
+        zero_hist();
+        __syncthreads();  // stage drained, histograms cleared
+        if (tid == 0) {
+            fence_proxy_async_smem();  // generic-proxy accesses of the stage happen-before the next TMA write
+            fetch(slot);
+        }
+        // the other stage's ticket was written at least one iteration (and one barrier) ago
+    }
+}
+
+template <typename KeyT> struct RingGeom;
+template <> struct RingGeom<uint32_t> { static constexpr int K = 16, WARPS = 16, LOOK = 16, STEP = 8; };
+template <> struct RingGeom<uint64_t> { static constexpr int K = 8,  WARPS = 16, LOOK = 16, STEP = 8; };
+
+template <typename KeyT, int RANK_MODE>
+static cudaError_t launch_ring_variant(const void* in, void* out, uint64_t n, uint32_t shift, const unsigned long long* gbase,
+                                       uint16_t* agg16, uint64_t* incl64, uint32_t* ticket, uint32_t epoch, int sm_count,
+                                       cudaStream_t stream)
+{
+    using G = RingGeom<KeyT>;
+    using S = RingSmem<KeyT, G::K, G::WARPS>;
+    const uint64_t tiles = (n + S::T - 1) / S::T;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * 2;
+    const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+    auto kern = digit_binning_ring_kernel<KeyT, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP>;
+    kern<<<grid, S::THREADS, sizeof(S), stream>>>(static_cast<const KeyT*>(in), static_cast<KeyT*>(out), n, shift, gbase, agg16,
+                                                   incl64, ticket, epoch, static_cast<uint32_t>(tiles));
+    return cudaGetLastError();
+}
+
+template <typename KeyT, int RANK_MODE>
+static cudaError_t set_ring_attr()
+{
+    using G = RingGeom<KeyT>;
+    using S = RingSmem<KeyT, G::K, G::WARPS>;
+    return cudaFuncSetAttribute(digit_binning_ring_kernel<KeyT, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+}
+
 // Geometry and lookback window.  Measured alternatives at n = 2^30 u32 keys (profiles/r01_geometry_experiments.txt,
 // profiles/r01_wide_kernel_experiments.txt), ms per pass: 16,384-key tiles on 2 x 512 threads per SM (this one) 2.80;
 // 8,192-key tiles, 3 CTAs/SM 5.46; 31,744-key tiles on 1 x 1024 threads 3.15; resident CTAs prefetching their next
@@ -868,6 +882,8 @@ static cudaError_t launch_tile_variant(const void* in, void* out, const uint32_t
 
 uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
 {
+    if (cfg.variant == kVariantPersistent && !pairs)
+        return key_bytes == 8 ? RingGeom<uint64_t>::K * RingGeom<uint64_t>::WARPS * 32 : RingGeom<uint32_t>::K * RingGeom<uint32_t>::WARPS * 32;
     if (cfg.variant == kVariantWide) {
         if (key_bytes == 8) return WideGeom<uint64_t, false>::K * WideGeom<uint64_t, false>::WARPS * 32;
         return pairs ? WideGeom<uint32_t, true>::K * WideGeom<uint32_t, true>::WARPS * 32
@@ -900,10 +916,10 @@ cudaError_t configure_kernels()
     if ((e = set_tile_attr<uint32_t, true, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint64_t, false, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint64_t, false, kRankBallot>()) != cudaSuccess) return e;
-    if ((e = set_persistent_attr<uint32_t, kRankAtomic>()) != cudaSuccess) return e;
-    if ((e = set_persistent_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
-    if ((e = set_persistent_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
-    if ((e = set_persistent_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_ring_attr<uint32_t, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_ring_attr<uint32_t, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_ring_attr<uint64_t, kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_ring_attr<uint64_t, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint32_t, false, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint32_t, false, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint32_t, true, kRankAtomic>()) != cudaSuccess) return e;
@@ -933,11 +949,11 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
     }
     if (cfg.variant == kVariantPersistent && !pairs) {
         if (key_bytes == 4)
-            return ballot ? launch_persistent_variant<uint32_t, kRankBallot>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream)
-                          : launch_persistent_variant<uint32_t, kRankAtomic>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream);
+            return ballot ? launch_ring_variant<uint32_t, kRankBallot>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, cfg.sm_count, stream)
+                          : launch_ring_variant<uint32_t, kRankAtomic>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, cfg.sm_count, stream);
         if (key_bytes == 8)
-            return ballot ? launch_persistent_variant<uint64_t, kRankBallot>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream)
-                          : launch_persistent_variant<uint64_t, kRankAtomic>(in, out, n, shift, gbase_place, desc, ticket, epoch, cfg.sm_count, stream);
+            return ballot ? launch_ring_variant<uint64_t, kRankBallot>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, cfg.sm_count, stream)
+                          : launch_ring_variant<uint64_t, kRankAtomic>(in, out, n, shift, gbase_place, agg16, desc, ticket, epoch, cfg.sm_count, stream);
     }
 #define OSB_DISPATCH(KEYT, PAIRS)                                                                                   \
     (ballot ? launch_tile_variant<KEYT, PAIRS, kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, desc,  \
