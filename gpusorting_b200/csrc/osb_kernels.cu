@@ -817,14 +817,21 @@ static cudaError_t set_ring_attr()
 // Geometry and lookback window.  Measured alternatives at n = 2^30 u32 keys (profiles/r01_geometry_experiments.txt,
 // profiles/r01_wide_kernel_experiments.txt), ms per pass: 16,384-key tiles on 2 x 512 threads per SM (this one) 2.80;
 // 8,192-key tiles, 3 CTAs/SM 5.46; 31,744-key tiles on 1 x 1024 threads 3.15; resident CTAs prefetching their next
-// tile's keys 3.08; run layout aligned for 16-byte vector stores 3.25.  Lookback window/probe spacing (whole sort, ms):
-// 8/4 11.71, 8/8 11.77, 16/4 11.89, 16/8 11.97, 24/8 12.06, 16/16 12.20, 32/8 12.99.
+// tile's keys 3.08; run layout aligned for 16-byte vector stores 3.25; 10,240-key tiles on 3 x 320 threads 2.74 (same);
+// 8,192-key tiles on 4 x 256 threads 2.89.  Every geometry that avoids spills lands on the same ~2.73 ms: the pass is
+// bound by the number of L1/shared-memory wavefronts per key, not by occupancy.  Lookback window/probe spacing (whole
+// sort, ms): 8/4 11.71, 8/2 11.78, 8/8 11.77, 4/2 11.82, 4/4 11.89, 16/4 11.89, 16/8 11.97, 24/8 12.06, 2/2 12.38, 32/8 12.99.
 #ifndef OSB_LOOK  // overridable for parameter sweeps (tools/sweep.sh)
 #define OSB_LOOK 8
 #define OSB_STEP 4
 #endif
 template <typename KeyT, bool PAIRS> struct WideGeom;
-template <> struct WideGeom<uint32_t, false> { static constexpr int K = 32, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
+#ifndef OSB_WIDE_WARPS  // geometry of the u32 keys-only kernel, overridable for sweeps
+#define OSB_WIDE_WARPS 16
+#define OSB_WIDE_K 32
+#define OSB_WIDE_MINB 2
+#endif
+template <> struct WideGeom<uint32_t, false> { static constexpr int K = OSB_WIDE_K, WARPS = OSB_WIDE_WARPS, MINB = OSB_WIDE_MINB, LOOK = OSB_LOOK, STEP = OSB_STEP; };
 template <> struct WideGeom<uint32_t, true>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
 template <> struct WideGeom<uint64_t, false> { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
 
