@@ -376,23 +376,22 @@ int osb200_digit_binning_pass(osb200_handle h, const void* d_in, void* d_out, co
     if (!d_in || !d_out || d_in == d_out) return OSB200_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(d_in) & 15u) || (reinterpret_cast<uintptr_t>(d_out) & 15u)) return OSB200_ERR_INVALID_ARG;
     if (n > h->max_n) return OSB200_ERR_SIZE;
-    if ((radix_shift & 7u) || radix_shift >= static_cast<uint32_t>(h->key_bytes) * 8u) return OSB200_ERR_INVALID_ARG;
+    if (radix_shift >= static_cast<uint32_t>(h->key_bytes) * 8u) return OSB200_ERR_INVALID_ARG;
     if ((d_in_values != nullptr) != (d_out_values != nullptr)) return OSB200_ERR_INVALID_ARG;
     if (d_in_values && (h->key_bytes != 4 || h->value_bytes != 4)) return OSB200_ERR_UNSUPPORTED;
     cudaStream_t q = static_cast<cudaStream_t>(stream);
-    const int place = static_cast<int>(radix_shift / 8u);
-    OSB_TRY(cudaMemsetAsync(h->control, 0, ControlLayout::zeroed_bytes, q));
-    // GlobalHistogram + Scan give every place; only `place` is consumed here
-    OSB_TRY(osb::launch_global_histogram(d_in, n, h->key_bytes, h->ghist(), h->sm_count, q));
-    OSB_TRY(osb::launch_scan(h->ghist(), h->gbase(), h->key_bytes, q));
-    uint32_t epoch = 0;
-    int st = next_epoch(h, q, &epoch);
+    // histogram of this digit only, then the pass (the reference's multiples of 8 and any other shift alike)
+    int st = osb_internal_digit_histogram(h, d_in, n, radix_shift, h->ghist(), q);
     if (st != OSB200_OK) return st;
+    OSB_TRY(cudaMemsetAsync(h->tickets(), 0, ControlLayout::ticket_bytes, q));
+    OSB_TRY(osb::launch_scan(h->ghist(), h->gbase(), 1, q));
     if (h->cfg.variant != osb::kVariantTilePerCta)
         OSB_TRY(cudaMemsetAsync(h->agg16, 0, h->desc_tiles * osb::kRadix * sizeof(uint16_t), q));
-    OSB_TRY(osb::launch_digit_binning(d_in, d_out, d_in_values, d_out_values, n, h->key_bytes, radix_shift,
-                                      h->gbase() + place * osb::kRadix, h->desc, h->agg16, h->tickets() + place, epoch,
-                                      h->cfg, q));
+    uint32_t epoch = 0;
+    st = next_epoch(h, q, &epoch);
+    if (st != OSB200_OK) return st;
+    OSB_TRY(osb::launch_digit_binning(d_in, d_out, d_in_values, d_out_values, n, h->key_bytes, radix_shift, h->gbase(), h->desc,
+                                      h->agg16, h->tickets(), epoch, h->cfg, q));
     return OSB200_OK;
 }
 

@@ -522,6 +522,7 @@ struct WideSmem {
     alignas(16) uint32_t hist[WARPS * kRadix];       // warp-private digit counters (counts, then running slots)
     unsigned long long keyptr[kRadix];               // per digit: byte address of out[first key of the digit - tile slot]
     unsigned long long valptr[PAIRS ? kRadix : 1];
+    uint32_t run[32];                                // few-bins scatter: first slot (low 16 bits) | live length (high 16)
     uint32_t wtot[kRadix / 32];
     uint32_t tile;
 };
@@ -612,11 +613,40 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
         const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
         sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
         if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
+        if (tid < 32) {
+            // the all-ones padding of the ragged last tile sits at the end of the run of its digit: not live
+            const uint32_t pad_digit = digit_of(static_cast<KeyT>(~static_cast<KeyT>(0)), shift);
+            const uint32_t live = tile_count - ((tid == pad_digit && !full) ? (T - valid) : 0u);
+            sm.run[tid] = tile_excl | (live << 16);
+        }
     }
     __syncthreads();
 
     // ---- scatter -----------------------------------------------------------------------------------------
-    if (full) {  // branch-free: all shared loads of the unrolled body can be in flight together
+    // Few bins (a pass on the top <= 5 bits: the sharded exchange on log2(R) bits): runs are thousands of keys long, so
+    // the stores are issued run by run in chunks that start on 128-byte boundaries of the DESTINATION -- every warp
+    // store is then one full line (4 full sectors), which is what keeps NVLink peer stores at their aligned rate
+    // (profiles/r01_p2p_store_ub.txt: 128-B aligned 680-716 GB/s vs 390-580 GB/s at 4-byte alignment).
+    constexpr uint32_t kKeyBits = sizeof(KeyT) * 8;
+    if (kKeyBits - shift <= 5) {
+        const uint32_t nbins = 1u << (kKeyBits - shift);
+        for (uint32_t b = 0; b < nbins; ++b) {
+            const uint32_t rd = sm.run[b];
+            const uint32_t lo = rd & 0xffffu, len = rd >> 16;
+            if (len == 0) continue;
+            const unsigned long long kp = sm.keyptr[b];
+            constexpr uint32_t kLine = 128 / sizeof(KeyT);  // keys per 128-byte line
+            const uint32_t ga = static_cast<uint32_t>((kp / sizeof(KeyT) + lo) & (kLine - 1));  // run start inside its line
+            const uint32_t total = len + ga;
+            for (uint32_t p = tid; p < total; p += THREADS) {
+                if (p >= ga) {
+                    const uint32_t x = lo + p - ga;
+                    st_stream(reinterpret_cast<KeyT*>(kp) + x, sm.sorted[x]);
+                    if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[b]) + x, sm.sorted_val[x]);
+                }
+            }
+        }
+    } else if (full) {  // branch-free: all shared loads of the unrolled body can be in flight together
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;

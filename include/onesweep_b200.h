@@ -99,7 +99,9 @@ OSB200_API int osb200_sort_host_keys_u64(osb200_handle h, uint64_t* h_keys, uint
  *   osb200_digit_binning_pass replaces OneSweep::Scan + one OneSweep::DigitBinningPassKeysOnly/Pairs
  *                             launch (Sort/OneSweep.cu:125-162,164-344,346-600): a stable counting
  *                             sort of d_in (and d_in_values, may be NULL) on the 8-bit digit at
- *                             `radix_shift` into d_out (d_out_values).  Out-of-place.
+ *                             `radix_shift` into d_out (d_out_values).  Out-of-place.  radix_shift is 0/8/16/24
+ *                             in the reference; any shift below the key width is accepted (a shift within 8
+ *                             bits of the top yields fewer than 256 bins -- the sharded exchange uses that).
  *   osb200_validate           replaces Validate<<<...>>> (UtilityKernels.cuh:403-429,432-479):
  *                             *h_err_count = number of adjacent inversions in d_keys (synchronises).
  * ---------------------------------------------------------------------------------------------- */

@@ -189,6 +189,27 @@ def test_single_digit_binning_pass(sorter, oracle):
     assert np.array_equal(host_u32(dst), wk) and np.array_equal(host_u32(dv), wv)
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_top_bits_pass_few_bins(sorter, oracle, variant):
+    """A pass on the top k <= 5 bits (what the sharded exchange runs): 2..32 bins, runs of thousands of keys."""
+    sorter.set_option("variant", variant)
+    try:
+        T = tile_keys(sorter)
+        for n in (3 * T + 1234, 1 << 20, 777):
+            k = oracle.init_random_u32(n, 0, 21 + n)
+            for shift in (31, 29, 27, 26, 13):
+                src, dst = dev_u32(k), torch.empty(n, dtype=torch.int32, device="cuda")
+                sorter.digit_binning_pass(src, dst, shift)
+                assert np.array_equal(host_u32(dst), oracle.binning_pass(k, shift)), f"n={n} shift={shift}"
+        # skew: everything in one top bin
+        k = oracle.init_random_u32(200000, 0, 5) | np.uint32(0xE0000000)
+        src, dst = dev_u32(k), torch.empty(k.size, dtype=torch.int32, device="cuda")
+        sorter.digit_binning_pass(src, dst, 29)
+        assert np.array_equal(host_u32(dst), oracle.binning_pass(k, 29))
+    finally:
+        sorter.set_option("variant", DEFAULT_VARIANT)
+
+
 def test_host_buffer_entry_points(g, oracle):
     s = g.OneSweepSorter(1 << 20, 4, 4)
     k = oracle.init_random_u32(1 << 20, 0, 31)
