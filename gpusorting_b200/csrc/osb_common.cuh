@@ -4,6 +4,7 @@
 // digit place, partition tile, tile reduction / inclusive prefix, chained scan with decoupled lookback.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 namespace osb {
@@ -53,6 +54,32 @@ __device__ __forceinline__ void st_relaxed_gpu_u64(uint64_t* p, uint64_t v)
 // descriptor words (which are re-read by successor tiles) from L1/L2 earlier than necessary.
 template <typename T> __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 template <typename T> __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
+
+// ---- typed keys: order-preserving bijection onto unsigned keys -----------------------------------------
+// The reference's CUDA path sorts uint32 only; its HLSL path sorts int/float keys by transforming their bits on the way
+// in and out (GPUSortingD3D12/Shaders/SortCommon.hlsl:134-154: FloatToUint / IntToUint and inverses) and reverses the
+// index on the last pass for descending order (:594-656, which reverses ties).  Here: encode(k) = k ^ m(k) ^ D with
+// m(k) = (sar(k) & A) | B; (A,B) = (0,0) unsigned, (0,SIGN) signed, (ALL,SIGN) IEEE float; D = ALL for descending
+// (complement: equal keys keep their input order, i.e. descending sorts are STABLE, unlike the reference's).
+struct KeyCodec {
+    unsigned long long a = 0, b = 0, d = 0;
+    uint32_t flags = 0;  // bit 0: encode keys right after loading; bit 1: decode keys right before storing
+};
+constexpr uint32_t kCodecEncodeOnLoad = 1u, kCodecDecodeOnStore = 2u;
+
+template <typename KeyT> __device__ __forceinline__ KeyT codec_encode(KeyT k, KeyT a, KeyT b, KeyT d)
+{
+    using S = typename std::make_signed<KeyT>::type;
+    const KeyT sar = static_cast<KeyT>(static_cast<S>(k) >> (sizeof(KeyT) * 8 - 1));
+    return k ^ (((sar & a) | b) ^ d);
+}
+template <typename KeyT> __device__ __forceinline__ KeyT codec_decode(KeyT e, KeyT a, KeyT b, KeyT d)
+{
+    using S = typename std::make_signed<KeyT>::type;
+    e ^= d;
+    const KeyT sar = static_cast<KeyT>(static_cast<S>(e) >> (sizeof(KeyT) * 8 - 1));
+    return e ^ ((~sar & a) | b);
+}
 
 template <typename KeyT> __device__ __forceinline__ uint32_t digit_of(KeyT k, uint32_t shift)
 {

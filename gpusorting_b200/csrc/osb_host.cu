@@ -109,7 +109,8 @@ int next_epoch(osb200_sorter* s, cudaStream_t stream, uint32_t* out)
 int check_handle(const osb200_sorter* s) { return s ? OSB200_OK : OSB200_ERR_INVALID_ARG; }
 
 // The launch plan (reference: OneSweepDispatcher.cuh:311-363).
-int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cudaStream_t stream)
+int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cudaStream_t stream,
+              const osb::KeyCodec* codec = nullptr)
 {
     if (n <= 1) return OSB200_OK;
     if (n > s->max_n) return OSB200_ERR_SIZE;
@@ -129,7 +130,9 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
     };
     s->ev_count = 0;
     OSB_TRY(mark());
-    OSB_TRY(osb::launch_global_histogram(d_keys, n, s->key_bytes, s->ghist(), s->sm_count, stream));
+    osb::KeyCodec enc;  // typed keys: the histogram and the first pass see encoded keys, the last pass stores them decoded
+    if (codec) { enc = *codec; enc.flags = osb::kCodecEncodeOnLoad; }
+    OSB_TRY(osb::launch_global_histogram(d_keys, n, s->key_bytes, s->ghist(), s->sm_count, stream, codec ? &enc : nullptr));
     OSB_TRY(mark());
     OSB_TRY(osb::launch_scan(s->ghist(), s->gbase(), places, stream));
     OSB_TRY(mark());
@@ -142,9 +145,14 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
         uint32_t epoch = 0;
         int st = next_epoch(s, stream, &epoch);
         if (st != OSB200_OK) return st;
+        osb::BinningConfig cfg = s->cfg;
+        if (codec) {
+            cfg.codec = *codec;
+            cfg.codec.flags = (p == 0 ? osb::kCodecEncodeOnLoad : 0u) | (p == places - 1 ? osb::kCodecDecodeOnStore : 0u);
+        }
         OSB_TRY(osb::launch_digit_binning(src, dst, sv, dv, n, s->key_bytes, static_cast<uint32_t>(p) * 8u,
                                           s->gbase() + p * osb::kRadix, s->desc, s->agg16 + p * agg_stride,
-                                          s->tickets() + p, epoch, s->cfg, stream));
+                                          s->tickets() + p, epoch, cfg, stream));
         OSB_TRY(mark());
         void* t = src; src = dst; dst = t;
         uint32_t* tv = sv; sv = dv; dv = tv;
@@ -332,6 +340,53 @@ int osb200_sort_keys_u64(osb200_handle h, uint64_t* d_keys, uint64_t n, void* st
 {
     if (check_handle(h) != OSB200_OK || h->key_bytes != 8) return OSB200_ERR_INVALID_ARG;
     return sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream));
+}
+
+// Typed keys.  key_type must match the handle's key width.
+static int make_codec(const osb200_sorter* h, int key_type, int descending, osb::KeyCodec* c)
+{
+    const bool wide64 = h->key_bytes == 8;
+    const unsigned long long all = wide64 ? ~0ull : 0xffffffffull, sign = wide64 ? (1ull << 63) : (1ull << 31);
+    switch (key_type) {
+        case OSB200_KEY_U32: if (wide64) return OSB200_ERR_INVALID_ARG; c->a = 0; c->b = 0; break;
+        case OSB200_KEY_I32: if (wide64) return OSB200_ERR_INVALID_ARG; c->a = 0; c->b = sign; break;
+        case OSB200_KEY_F32: if (wide64) return OSB200_ERR_INVALID_ARG; c->a = all; c->b = sign; break;
+        case OSB200_KEY_U64: if (!wide64) return OSB200_ERR_INVALID_ARG; c->a = 0; c->b = 0; break;
+        case OSB200_KEY_I64: if (!wide64) return OSB200_ERR_INVALID_ARG; c->a = 0; c->b = sign; break;
+        case OSB200_KEY_F64: if (!wide64) return OSB200_ERR_INVALID_ARG; c->a = all; c->b = sign; break;
+        default: return OSB200_ERR_INVALID_ARG;
+    }
+    c->d = descending ? all : 0;
+    c->flags = 0;
+    return OSB200_OK;
+}
+
+int osb200_sort_keys_typed(osb200_handle h, void* d_keys, uint64_t n, int key_type, int descending, void* stream)
+{
+    if (check_handle(h) != OSB200_OK) return OSB200_ERR_INVALID_ARG;
+    osb::KeyCodec c;
+    int st = make_codec(h, key_type, descending, &c);
+    if (st != OSB200_OK) return st;
+    if (h->cfg.variant != osb::kVariantWide) return OSB200_ERR_UNSUPPORTED;
+    const bool plain = c.a == 0 && c.b == 0 && c.d == 0;
+    const int vb = h->value_bytes;
+    h->value_bytes = 0;
+    st = sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream), plain ? nullptr : &c);
+    h->value_bytes = vb;
+    return st;
+}
+
+int osb200_sort_pairs_typed(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int key_type, int descending,
+                            void* stream)
+{
+    if (check_handle(h) != OSB200_OK || h->key_bytes != 4 || h->value_bytes != 4) return OSB200_ERR_INVALID_ARG;
+    if (n > 1 && !d_values) return OSB200_ERR_INVALID_ARG;
+    osb::KeyCodec c;
+    int st = make_codec(h, key_type, descending, &c);
+    if (st != OSB200_OK) return st;
+    if (h->cfg.variant != osb::kVariantWide) return OSB200_ERR_UNSUPPORTED;
+    const bool plain = c.a == 0 && c.b == 0 && c.d == 0;
+    return sort_impl(h, d_keys, d_values, n, static_cast<cudaStream_t>(stream), plain ? nullptr : &c);
 }
 
 int osb200_sort_host_keys_u32(osb200_handle h, uint32_t* h_keys, uint64_t n)

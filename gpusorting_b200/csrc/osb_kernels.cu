@@ -45,6 +45,22 @@ __device__ __forceinline__ void hist_count_word(uint32_t* s_col, uint32_t w, int
     }
 }
 
+// typed keys: histogram the ENCODED keys (the passes see them encoded)
+template <typename KeyT>
+__device__ __forceinline__ uint4 hist_encode_vec(uint4 v, const KeyCodec& c)
+{
+    if constexpr (sizeof(KeyT) == 4) {
+        const uint32_t a = static_cast<uint32_t>(c.a), b = static_cast<uint32_t>(c.b), d = static_cast<uint32_t>(c.d);
+        v.x = codec_encode<uint32_t>(v.x, a, b, d); v.y = codec_encode<uint32_t>(v.y, a, b, d);
+        v.z = codec_encode<uint32_t>(v.z, a, b, d); v.w = codec_encode<uint32_t>(v.w, a, b, d);
+    } else {
+        unsigned long long k0 = (static_cast<unsigned long long>(v.y) << 32) | v.x, k1 = (static_cast<unsigned long long>(v.w) << 32) | v.z;
+        k0 = codec_encode<unsigned long long>(k0, c.a, c.b, c.d); k1 = codec_encode<unsigned long long>(k1, c.a, c.b, c.d);
+        v.x = static_cast<uint32_t>(k0); v.y = static_cast<uint32_t>(k0 >> 32); v.z = static_cast<uint32_t>(k1); v.w = static_cast<uint32_t>(k1 >> 32);
+    }
+    return v;
+}
+
 template <typename KeyT>
 __device__ __forceinline__ void hist_count_vec(uint32_t* s_col, const uint4& v)
 {
@@ -56,7 +72,7 @@ __device__ __forceinline__ void hist_count_vec(uint32_t* s_col, const uint4& v)
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kHistThreads, 1)
-global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ ghist)
+global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ ghist, KeyCodec codec)
 {
     constexpr int PLACES = sizeof(KeyT);
     constexpr int VEC = 16 / sizeof(KeyT);
@@ -71,25 +87,29 @@ global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long
     const uint4* __restrict__ vp = reinterpret_cast<const uint4*>(keys);
     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kHistThreads;
     uint64_t i = static_cast<uint64_t>(blockIdx.x) * kHistThreads + threadIdx.x;
+    const bool enc = codec.flags & kCodecEncodeOnLoad;
     for (; i + 3 * stride < nvec; i += 4 * stride) {
-        const uint4 a = __ldcs(vp + i);
-        const uint4 b = __ldcs(vp + i + stride);
-        const uint4 c = __ldcs(vp + i + 2 * stride);
-        const uint4 d = __ldcs(vp + i + 3 * stride);
+        uint4 a = __ldcs(vp + i);
+        uint4 b = __ldcs(vp + i + stride);
+        uint4 c = __ldcs(vp + i + 2 * stride);
+        uint4 d = __ldcs(vp + i + 3 * stride);
+        if (enc) { a = hist_encode_vec<KeyT>(a, codec); b = hist_encode_vec<KeyT>(b, codec); c = hist_encode_vec<KeyT>(c, codec); d = hist_encode_vec<KeyT>(d, codec); }
         hist_count_vec<KeyT>(s_col, a);
         hist_count_vec<KeyT>(s_col, b);
         hist_count_vec<KeyT>(s_col, c);
         hist_count_vec<KeyT>(s_col, d);
     }
     for (; i < nvec; i += stride) {
-        const uint4 a = __ldcs(vp + i);
+        uint4 a = __ldcs(vp + i);
+        if (enc) a = hist_encode_vec<KeyT>(a, codec);
         hist_count_vec<KeyT>(s_col, a);
     }
     // ragged tail (n not a multiple of the vector width)
     if (blockIdx.x == 0) {
         const uint64_t t = nvec * VEC + threadIdx.x;
         if (t < n) {
-            const KeyT k = keys[t];
+            KeyT k = keys[t];
+            if (enc) k = codec_encode<KeyT>(k, static_cast<KeyT>(codec.a), static_cast<KeyT>(codec.b), static_cast<KeyT>(codec.d));
 #pragma unroll
             for (int p = 0; p < PLACES; ++p)
                 atomicAdd(&s_col[(p * kRadix + (static_cast<uint32_t>(k >> (8 * p)) & 255u)) * COLS], 1u);
@@ -108,18 +128,19 @@ global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long
 template <typename KeyT> constexpr size_t hist_smem_bytes() { return sizeof(KeyT) * kRadix * HistGeom<KeyT>::COLS * sizeof(uint32_t); }
 
 cudaError_t launch_global_histogram(const void* keys, uint64_t n, int key_bytes, unsigned long long* ghist,
-                                    int sm_count, cudaStream_t stream)
+                                    int sm_count, cudaStream_t stream, const KeyCodec* codec_in)
 {
+    const KeyCodec codec = codec_in ? *codec_in : KeyCodec();
     const uint64_t vecs = n / (16 / key_bytes);
     uint64_t want = (vecs + kHistThreads - 1) / kHistThreads;
     if (want < 1) want = 1;
     const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) ? want : sm_count);
     if (key_bytes == 4)
         global_histogram_kernel<uint32_t><<<grid, kHistThreads, hist_smem_bytes<uint32_t>(), stream>>>(
-            static_cast<const uint32_t*>(keys), n, ghist);
+            static_cast<const uint32_t*>(keys), n, ghist, codec);
     else
         global_histogram_kernel<uint64_t><<<grid, kHistThreads, hist_smem_bytes<uint64_t>(), stream>>>(
-            static_cast<const uint64_t*>(keys), n, ghist);
+            static_cast<const uint64_t*>(keys), n, ghist, codec);
     return cudaGetLastError();
 }
 
@@ -533,7 +554,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, const uint32_t* __restrict__ in_val,
                           uint32_t* __restrict__ out_val, uint64_t n, uint32_t shift,
                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
-                          uint32_t* ticket, uint32_t epoch)
+                          uint32_t* ticket, uint32_t epoch, KeyCodec codec)
 {
     using S = WideSmem<KeyT, PAIRS, K, WARPS>;
     constexpr int THREADS = S::THREADS;
@@ -577,6 +598,18 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
         }
     }
 
+    // typed keys: the first pass of a sort turns the caller's keys into order-equivalent unsigned keys.  The padding of
+    // the ragged last tile is encoded too and stays the largest key only if it was loaded as the pre-image of all-ones,
+    // so it is simply re-set after encoding.
+    if (codec.flags & kCodecEncodeOnLoad) {
+        const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            key[i] = codec_encode<KeyT>(key[i], ca, cb, cd);
+            if (!full && warp_off + i * 32 >= valid) key[i] = static_cast<KeyT>(~static_cast<KeyT>(0));
+        }
+    }
+
     // ---- phase 1: count digits per warp (order-free, non-returning atomics) ---------------------------
 #pragma unroll
     for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift)], 1u);
@@ -598,6 +631,8 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     __syncthreads();
 
     // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -----------------
+    // (typed keys: the last pass stores the keys decoded; the digit was taken from the encoded key, and the scatter
+    // below re-derives it from the tile, so the decoded form is produced only at the very end, in the store)
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
@@ -641,12 +676,14 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
             for (uint32_t p = tid; p < total; p += THREADS) {
                 if (p >= ga) {
                     const uint32_t x = lo + p - ga;
-                    st_stream(reinterpret_cast<KeyT*>(kp) + x, sm.sorted[x]);
+                    KeyT k = sm.sorted[x];
+                    if (codec.flags & kCodecDecodeOnStore) k = codec_decode<KeyT>(k, static_cast<KeyT>(codec.a), static_cast<KeyT>(codec.b), static_cast<KeyT>(codec.d));
+                    st_stream(reinterpret_cast<KeyT*>(kp) + x, k);
                     if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[b]) + x, sm.sorted_val[x]);
                 }
             }
         }
-    } else if (full) {  // branch-free: all shared loads of the unrolled body can be in flight together
+    } else if (full && !(codec.flags & kCodecDecodeOnStore)) {  // branch-free: all shared loads of the unrolled body in flight together
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;
@@ -655,14 +692,16 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
             st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
             if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
         }
-    } else {
+    } else {  // ragged last tile, or the last pass of a typed sort (keys leave decoded)
+        const bool dec = codec.flags & kCodecDecodeOnStore;
+        const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
 #pragma unroll 4
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;
             if (idx < valid) {
                 const KeyT k = sm.sorted[idx];
                 const uint32_t d = digit_of(k, shift);
-                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
+                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, dec ? codec_decode<KeyT>(k, ca, cb, cd) : k);
                 if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
             }
         }
@@ -868,14 +907,15 @@ template <> struct WideGeom<uint64_t, false> { static constexpr int K = 16, WARP
 template <typename KeyT, bool PAIRS, int RANK_MODE>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
                                        uint32_t shift, const unsigned long long* gbase, uint16_t* agg16, uint64_t* incl64,
-                                       uint32_t* ticket, uint32_t epoch, cudaStream_t stream)
+                                       uint32_t* ticket, uint32_t epoch, const KeyCodec& codec, cudaStream_t stream)
 {
     using G = WideGeom<KeyT, PAIRS>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
     const uint64_t tiles = (n + S::T - 1) / S::T;
     auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>;
     kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
-        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch);
+        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch,
+        codec);
     return cudaGetLastError();
 }
 
@@ -973,12 +1013,13 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
+    if (cfg.codec.flags && cfg.variant != kVariantWide) return cudaErrorNotSupported;  // typed keys: default kernel only
     if (cfg.variant == kVariantWide) {
 #define OSB_WIDE(KEYT, PAIRS)                                                                                          \
     (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
-                                                           ticket, epoch, stream)                                      \
+                                                           ticket, epoch, cfg.codec, stream)                           \
             : launch_wide_variant<KEYT, PAIRS, kRankAtomic>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
-                                                           ticket, epoch, stream))
+                                                           ticket, epoch, cfg.codec, stream))
         if (key_bytes == 4) return pairs ? OSB_WIDE(uint32_t, true) : OSB_WIDE(uint32_t, false);
         if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false);
 #undef OSB_WIDE

@@ -3,6 +3,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "osb_common.cuh"
+
 namespace osb {
 
 // Kernel variants of the digit-binning pass (osb200_set_option "variant").
@@ -21,6 +23,7 @@ struct BinningConfig {
     int variant = kVariantTilePerCta;
     int rank_mode = kRankAtomic;
     int sm_count = 148;
+    KeyCodec codec;  // typed keys: encode-on-load / decode-on-store for THIS launch (flags 0 = plain unsigned keys)
 };
 
 // keys per partition tile for a key width / pairs flag / variant (host needs it to size descriptors)
@@ -32,7 +35,7 @@ cudaError_t configure_kernels();
 // GlobalHistogram (reference: OneSweep::GlobalHistogram, Sort/OneSweep.cu:44-123).
 // ghist[place*256 + digit] += counts; caller zeroes ghist first.
 cudaError_t launch_global_histogram(const void* keys, uint64_t n, int key_bytes, unsigned long long* ghist,
-                                    int sm_count, cudaStream_t stream);
+                                    int sm_count, cudaStream_t stream, const KeyCodec* codec = nullptr);
 
 // Single-place histogram (used by the sharded path for the most significant digit): hist256[digit] += counts.
 cudaError_t launch_digit_histogram(const void* keys, uint64_t n, int key_bytes, uint32_t shift,

@@ -23,8 +23,9 @@ from ._lib import check, lib
 
 ENTROPY_PRESET_1, ENTROPY_PRESET_2, ENTROPY_PRESET_3, ENTROPY_PRESET_4, ENTROPY_PRESET_5 = range(5)
 
-_KEY_DTYPES_4 = (torch.int32, torch.uint32)
-_KEY_DTYPES_8 = (torch.int64, torch.uint64)
+_KEY_DTYPES_4 = (torch.int32, torch.uint32, torch.float32)
+_KEY_DTYPES_8 = (torch.int64, torch.uint64, torch.float64)
+KEY_TYPES = {"u32": 0, "i32": 1, "f32": 2, "u64": 3, "i64": 4, "f64": 5}
 
 
 def _stream_ptr(stream: Optional[torch.cuda.Stream]) -> int:
@@ -100,6 +101,25 @@ class OneSweepSorter:
             _check_dev_tensor(keys, _KEY_DTYPES_8, "keys")
             check(lib.osb200_sort_keys_u64(self._h, keys.data_ptr(), n, _stream_ptr(stream)), "osb200_sort_keys_u64")
         return keys
+
+    def sort_keys_typed(self, keys: torch.Tensor, key_type: str, descending: bool = False, n: Optional[int] = None,
+                        stream=None) -> torch.Tensor:
+        """Signed / float keys and descending order (reference HLSL: SortCommon.hlsl:134-154,594-656).  key_type in
+        KEY_TYPES; it states how the bits are ordered, whatever the tensor dtype (which only has to have the width)."""
+        n = keys.numel() if n is None else int(n)
+        _check_dev_tensor(keys, _KEY_DTYPES_4 if self.key_bytes == 4 else _KEY_DTYPES_8, "keys")
+        check(lib.osb200_sort_keys_typed(self._h, keys.data_ptr(), n, KEY_TYPES[key_type], 1 if descending else 0,
+                                         _stream_ptr(stream)), "osb200_sort_keys_typed")
+        return keys
+
+    def sort_pairs_typed(self, keys: torch.Tensor, values: torch.Tensor, key_type: str, descending: bool = False,
+                         n: Optional[int] = None, stream=None):
+        n = keys.numel() if n is None else int(n)
+        _check_dev_tensor(keys, _KEY_DTYPES_4, "keys")
+        _check_dev_tensor(values, _KEY_DTYPES_4, "values")
+        check(lib.osb200_sort_pairs_typed(self._h, keys.data_ptr(), values.data_ptr(), n, KEY_TYPES[key_type],
+                                          1 if descending else 0, _stream_ptr(stream)), "osb200_sort_pairs_typed")
+        return keys, values
 
     def sort_pairs(self, keys: torch.Tensor, values: torch.Tensor, n: Optional[int] = None, stream=None):
         n = keys.numel() if n is None else int(n)

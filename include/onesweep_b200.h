@@ -84,6 +84,19 @@ OSB200_API int osb200_sort_keys_u32(osb200_handle h, uint32_t* d_keys, uint64_t 
 OSB200_API int osb200_sort_pairs_u32(osb200_handle h, uint32_t* d_keys, uint32_t* d_values, uint64_t n, void* stream);
 OSB200_API int osb200_sort_keys_u64(osb200_handle h, uint64_t* d_keys, uint64_t n, void* stream);
 
+/* Typed keys and descending order (the reference has them only in its HLSL path: IntToUint / FloatToUint and inverses,
+ * GPUSortingD3D12/Shaders/SortCommon.hlsl:134-154; descending :594-656).  The order-preserving bit transform is fused
+ * into the first pass (and the histogram) and undone in the last pass's stores: no extra traffic.  Floats follow the
+ * IEEE total order of their bit patterns (-0.0 < +0.0, NaNs at the ends), as the reference's transform does.
+ * Descending is the complement of the transformed key, so equal keys KEEP their input order (stable) -- unlike the
+ * reference's index reversal, which reverses ties.  key_type must match the handle's key width. */
+typedef enum osb200_key_type {
+    OSB200_KEY_U32 = 0, OSB200_KEY_I32 = 1, OSB200_KEY_F32 = 2, OSB200_KEY_U64 = 3, OSB200_KEY_I64 = 4, OSB200_KEY_F64 = 5
+} osb200_key_type;
+OSB200_API int osb200_sort_keys_typed(osb200_handle h, void* d_keys, uint64_t n, int key_type, int descending, void* stream);
+OSB200_API int osb200_sort_pairs_typed(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int key_type,
+                                       int descending, void* stream);
+
 /* Host-buffer entry points: copy in, sort, copy back, synchronise.  `h_*` may be pageable or pinned
  * host memory.  This is the end-to-end call a host-side caller of the reference would make (the
  * reference itself has no host-data API; its buffers are generated on the device,
