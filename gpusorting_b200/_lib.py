@@ -8,6 +8,11 @@ from __future__ import annotations
 import ctypes
 import os
 
+# torch must be imported BEFORE the shared library is loaded: libonesweep_b200.so needs libnccl.so.2 (sharded sort) and the
+# dynamic loader binds one library per soname per process -- torch ships a newer NCCL than the system one, and
+# libtorch_cuda.so fails to load ("undefined symbol ncclDevCommCreate") if the older system copy got in first.
+import torch  # noqa: F401
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OSB200_LIB") or os.path.join(_HERE, "lib", "libonesweep_b200.so")  # override: build sweeps only
 
