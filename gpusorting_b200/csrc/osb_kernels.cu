@@ -7,7 +7,7 @@
 //
 // The B200 design point: at ~23 B/clk/SM of HBM bandwidth a binning pass must retire
 // ~2.3 keys per SM clock, which the reference's 8-ballots-per-key warp multisplit cannot issue (measured
-// 2.1 keys/clk/SM for the ballots alone, profiles/r01_microbench.md).  Ranking is therefore done with ONE
+// 2.1 keys/clk/SM for the ballots alone, profiles/r01_microbench_rank.txt).  Ranking is therefore done with ONE
 // shared-memory atomicAdd per key on a warp-private histogram: on sm_100 the returning ATOMS.ADD hands its
 // values to same-address lanes of a warp instruction in ascending lane order (verified over 5e10 atomics and
 // re-verified by a device self-test when a sorter is created), i.e. it is a single-instruction stable
