@@ -129,11 +129,17 @@ def cpu_baseline(threads_hint: int = 0):
     t0 = time.perf_counter()
     orc.lib.orc_std_sort_u32(w2.ctypes.data, m)
     std_dt = time.perf_counter() - t0
+    np.copyto(work, src)
+    t0 = time.perf_counter()
+    orc.lib.orc_parallel_sort_u32(work.ctypes.data, n, threads)  # libstdc++ parallel-mode std::sort, all cores
+    par_dt = time.perf_counter() - t0
     return {
         "value": round(n / best / 1e9, 4), "unit": "Gkeys/s", "cores": threads, "kind": "port",
         "sample": f"2^{CPU_SAMPLE_LOG2} of the 2^{LOG2_N} uint32 keys (InitRandom seed {SEED}); host-parallel 4-pass LSD "
                   f"radix port of OneSweep (oracle/oracle.c orc_onesweep_parallel), best of 3",
         "std_sort_1_thread_gkeys_s": round(m / std_dt / 1e9, 4), "std_sort_sample": "2^24 keys, std::sort, 1 thread",
+        "gnu_parallel_sort_gkeys_s": round(n / par_dt / 1e9, 4),
+        "gnu_parallel_sort_sample": f"2^{CPU_SAMPLE_LOG2} keys, __gnu_parallel::sort, {threads} threads",
     }
 
 
