@@ -130,3 +130,17 @@ int main() {
         assert r.returncode == 0, r.stderr
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_host_side_units_of_the_device_headers():
+    """tests/host_unit.cu: descriptor packing and the typed-key codec, compiled with nvcc and run on the CPU."""
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "host_unit")
+        r = subprocess.run(["nvcc", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "host_unit.cu")],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and "host_unit: ok" in r.stdout, r.stdout + r.stderr
