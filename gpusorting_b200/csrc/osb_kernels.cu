@@ -534,6 +534,13 @@ lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint
     }
 }
 
+// OSB_EXP: compile-time experiments for tools/sweep.sh, OFF (0) in the product build.  Not yet measured on hardware:
+//   bit 0 (1): 32-bit element offsets per digit instead of 64-bit byte pointers in the scatter (valid for n <= 2^32, out != 0)
+//   bit 1 (2): 256-bin passes store run by run, warp-owned digits, in chunks aligned to the destination's 128-byte lines
+#ifndef OSB_EXP
+#define OSB_EXP 0
+#endif
+
 template <typename KeyT, bool PAIRS, int K, int WARPS>
 struct WideSmem {
     static constexpr int THREADS = WARPS * 32;
@@ -543,7 +550,13 @@ struct WideSmem {
     alignas(16) uint32_t hist[WARPS * kRadix];       // warp-private digit counters (counts, then running slots)
     unsigned long long keyptr[kRadix];               // per digit: byte address of out[first key of the digit - tile slot]
     unsigned long long valptr[PAIRS ? kRadix : 1];
-    uint32_t run[32];                                // few-bins scatter: first slot (low 16 bits) | live length (high 16)
+    uint32_t run[(OSB_EXP & 2) ? kRadix : 32];       // run-by-run scatter: first slot (low 16 bits) | live length (high 16)
+#if OSB_EXP & 1
+    uint32_t off32[kRadix];                          // element index of tile slot 0 "as if" of this digit, mod 2^32
+#endif
+#if OSB_EXP & 2
+    uint32_t longmask[kRadix / 32];                  // digits whose run is long enough to be stored by the whole CTA
+#endif
     uint32_t wtot[kRadix / 32];
     uint32_t tile;
 };
@@ -648,12 +661,19 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
         const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
         sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
         if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
-        if (tid < 32) {
+        if (tid < 32 || (OSB_EXP & 2)) {
             // the all-ones padding of the ragged last tile sits at the end of the run of its digit: not live
             const uint32_t pad_digit = digit_of(static_cast<KeyT>(~static_cast<KeyT>(0)), shift);
             const uint32_t live = tile_count - ((tid == pad_digit && !full) ? (T - valid) : 0u);
             sm.run[tid] = tile_excl | (live << 16);
+#if OSB_EXP & 2
+            const uint32_t lm = __ballot_sync(0xffffffffu, live > 1024u);
+            if (lane == 0) sm.longmask[warp] = lm;
+#endif
         }
+#if OSB_EXP & 1
+        sm.off32[tid] = static_cast<uint32_t>(first);
+#endif
     }
     __syncthreads();
 
@@ -683,6 +703,47 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
                 }
             }
         }
+#if OSB_EXP & 2
+    } else if (full && !(codec.flags & kCodecDecodeOnStore) && !PAIRS) {
+        // (experiment) every warp stores the runs of "its" digits, chunk-aligned to the destination lines ...
+        constexpr uint32_t kLine = 128 / sizeof(KeyT);
+        for (uint32_t d = warp; d < kRadix; d += WARPS) {
+            const uint32_t rd = sm.run[d];
+            const uint32_t lo = rd & 0xffffu, len = rd >> 16;
+            if (len == 0 || len > 1024u) continue;
+            const unsigned long long kp = sm.keyptr[d];
+            const uint32_t ga = static_cast<uint32_t>((kp / sizeof(KeyT) + lo) & (kLine - 1));
+            const uint32_t total = len + ga;
+            for (uint32_t p = lane; p < total; p += 32) {
+                if (p >= ga) { const uint32_t x = lo + p - ga; st_stream(reinterpret_cast<KeyT*>(kp) + x, sm.sorted[x]); }
+            }
+        }
+        // ... and runs longer than 1024 keys (skewed inputs) are stored by the whole CTA, as in the few-bins path
+        for (uint32_t wd = 0; wd < kRadix / 32; ++wd) {
+            uint32_t m = sm.longmask[wd];
+            while (m) {
+                const uint32_t d = wd * 32 + (__ffs(m) - 1);
+                m &= m - 1;
+                const uint32_t rd = sm.run[d];
+                const uint32_t lo = rd & 0xffffu, len = rd >> 16;
+                const unsigned long long kp = sm.keyptr[d];
+                const uint32_t ga = static_cast<uint32_t>((kp / sizeof(KeyT) + lo) & (kLine - 1));
+                const uint32_t total = len + ga;
+                for (uint32_t p = tid; p < total; p += THREADS) {
+                    if (p >= ga) { const uint32_t x = lo + p - ga; st_stream(reinterpret_cast<KeyT*>(kp) + x, sm.sorted[x]); }
+                }
+            }
+        }
+#endif
+#if OSB_EXP & 1
+    } else if (full && !(codec.flags & kCodecDecodeOnStore) && !PAIRS && out != nullptr) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            const KeyT k = sm.sorted[idx];
+            st_stream(out + static_cast<uint32_t>(sm.off32[digit_of(k, shift)] + idx), k);
+        }
+#endif
     } else if (full && !(codec.flags & kCodecDecodeOnStore)) {  // branch-free: all shared loads of the unrolled body in flight together
 #pragma unroll
         for (int j = 0; j < K; ++j) {
