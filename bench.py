@@ -30,7 +30,38 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+def _physical_cores() -> int:
+    """Physical cores this process may run on (affinity mask, one per SMT sibling set)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+    seen = set()
+    for c in cpus:
+        try:
+            sib = open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip()
+        except OSError:
+            sib = str(c)
+        seen.add(sib)
+    return max(1, len(seen))
+
+
+HOST_THREADS = _physical_cores()
+# The CPU legs use every physical core, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1).  Must happen
+# before numpy / torch / the oracle load an OpenMP runtime.
+os.environ["OMP_NUM_THREADS"] = str(HOST_THREADS)
+os.environ.setdefault("OMP_PROC_BIND", "spread")
+os.environ.setdefault("OMP_PLACES", "cores")
+
 LOG2_N = 30            # BASELINE.json configs[1]: 2^30 uint32 keys-only, uniform random, 1xB200
+METRIC = "OneSweep sort throughput, 2^30 uint32 keys per GPU, keys-only, uniform-random"  # both arms print this string
+DATA = "synthetic (reference InitRandom generator, seed 10, entropy preset 1)"
+
+
+def workload(log2n: int, world: int) -> str:
+    w = f"2^{log2n} uint32 keys-only OneSweep per GPU, uniform-random (BASELINE.json configs[1])"
+    return w if world == 1 else w + f"; {world} GPUs: MSD bucket exchange over NVLink then local OneSweep"
+
 SEED = 10              # the reference's benchmark seed (GPUSortingCUDA.cu:22)
 CPU_SAMPLE_LOG2 = 27   # bounded CPU sample of the same workload (1/8 of it)
 ALG_BYTES_PER_KEY_PER_PASS = 8  # SURVEY 8(d): one DigitBinningPass reads 4 B and writes 4 B per key
@@ -104,8 +135,9 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def cpu_baseline(threads_hint: int = 0):
-    """Bounded CPU sample: the oracle's host-parallel OneSweep port on all cores + std::sort on one core."""
+def _cpu_sort_sample(steps: int, warmup: int):
+    """The CPU leg shared by cpu_baseline and --impl reference: the oracle's host-parallel OneSweep port on
+    HOST_THREADS threads over a 2^CPU_SAMPLE_LOG2-key sample of the workload.  Returns (best_s, mean_s, all_s, orc, src)."""
     from tests import oraclelib
     import numpy as np
 
@@ -114,70 +146,70 @@ def cpu_baseline(threads_hint: int = 0):
     src = orc.init_random_u32(n, 0, SEED)
     work = src.copy()
     alt = np.zeros_like(src)  # pre-faulted scratch: page faults are not part of the sort
-    threads = orc.host_threads()
-    orc.sort_parallel_inplace(work, threads=0, alt=alt)  # warm-up (thread pool)
-    best = None
-    for _ in range(3):
+    for _ in range(max(warmup, 1)):
+        np.copyto(work, src)
+        orc.sort_parallel_inplace(work, threads=HOST_THREADS, alt=alt)
+    times = []
+    for _ in range(max(steps, 1)):
         np.copyto(work, src)
         t0 = time.perf_counter()
-        orc.sort_parallel_inplace(work, threads=0, alt=alt)
-        dt = time.perf_counter() - t0
-        best = dt if best is None or dt < best else best
+        orc.sort_parallel_inplace(work, threads=HOST_THREADS, alt=alt)
+        times.append(time.perf_counter() - t0)
     assert orc.validate(work) == 0
+    return min(times), sum(times) / len(times), times, orc, src
+
+
+def _sample_text(kind: str) -> str:
+    return (f"2^{CPU_SAMPLE_LOG2} of the 2^{LOG2_N} uint32 keys (1/{1 << (LOG2_N - CPU_SAMPLE_LOG2)} of the workload, InitRandom "
+            f"seed {SEED}) per step; host-parallel 4-pass LSD radix port of OneSweep (oracle/oracle.c orc_onesweep_parallel) "
+            f"on {HOST_THREADS} threads = physical cores of the affinity mask, OMP_PROC_BIND={os.environ.get('OMP_PROC_BIND')}; {kind}")
+
+
+def cpu_baseline():
+    """Bounded CPU sample: the oracle's host-parallel OneSweep port on all physical cores + std::sort on one core."""
+    import numpy as np
+
+    best, mean, times, orc, src = _cpu_sort_sample(steps=5, warmup=1)
+    n = src.size
     m = 1 << 24
     w2 = src[:m].copy()
     t0 = time.perf_counter()
     orc.lib.orc_std_sort_u32(w2.ctypes.data, m)
     std_dt = time.perf_counter() - t0
-    np.copyto(work, src)
+    work = src.copy()
     t0 = time.perf_counter()
-    orc.lib.orc_parallel_sort_u32(work.ctypes.data, n, threads)  # libstdc++ parallel-mode std::sort, all cores
+    orc.lib.orc_parallel_sort_u32(work.ctypes.data, n, HOST_THREADS)  # libstdc++ parallel-mode std::sort, all cores
     par_dt = time.perf_counter() - t0
     return {
-        "value": round(n / best / 1e9, 4), "unit": "Gkeys/s", "cores": threads, "kind": "port",
-        "sample": f"2^{CPU_SAMPLE_LOG2} of the 2^{LOG2_N} uint32 keys (InitRandom seed {SEED}); host-parallel 4-pass LSD "
-                  f"radix port of OneSweep (oracle/oracle.c orc_onesweep_parallel), best of 3",
+        "value": round(n / best / 1e9, 4), "unit": "Gkeys/s", "cores": HOST_THREADS, "kind": "port",
+        "sample": _sample_text("best of 5"), "mean_gkeys_s": round(n / mean / 1e9, 4),
         "std_sort_1_thread_gkeys_s": round(m / std_dt / 1e9, 4), "std_sort_sample": "2^24 keys, std::sort, 1 thread",
         "gnu_parallel_sort_gkeys_s": round(n / par_dt / 1e9, 4),
-        "gnu_parallel_sort_sample": f"2^{CPU_SAMPLE_LOG2} keys, __gnu_parallel::sort, {threads} threads",
+        "gnu_parallel_sort_sample": f"2^{CPU_SAMPLE_LOG2} keys, __gnu_parallel::sort, {HOST_THREADS} threads",
     }
 
 
 def run_reference_arm(args, rank, world, emit):
-    """--impl reference: the CPU leg (rank 0 only; other ranks exit 0 without work)."""
+    """--impl reference: the CPU leg (rank 0 only; other ranks exit 0 without work).  The reference has no CPU
+    implementation of this path and its CUDA kernels are not a CPU arm, so this times the oracle's
+    host-parallel port of the same algorithm.  value = best of the K timed steps (the most favourable number for the
+    CPU side; the mean is reported beside it)."""
     if rank != 0:
         return
-    from tests import oraclelib
-    import numpy as np
-
-    orc = oraclelib.load_oracle()
-    n = 1 << CPU_SAMPLE_LOG2
-    threads = orc.host_threads()
-    src = orc.init_random_u32(n, 0, SEED)
-    work = src.copy()
-    alt = np.zeros_like(src)  # pre-faulted scratch
-    for _ in range(max(args.warmup, 1)):
-        np.copyto(work, src)
-        orc.sort_parallel_inplace(work, threads=0, alt=alt)
-    total = 0.0
-    for _ in range(args.steps):
-        np.copyto(work, src)
-        t0 = time.perf_counter()
-        orc.sort_parallel_inplace(work, threads=0, alt=alt)
-        total += time.perf_counter() - t0
-    assert orc.validate(work) == 0
-    ms = total / args.steps * 1e3
-    value = n / (ms / 1e3) / 1e9
-    sample = (f"each step sorts a 2^{CPU_SAMPLE_LOG2}-key sample (1/{1 << (LOG2_N - CPU_SAMPLE_LOG2)}) of the 2^{LOG2_N}-key "
-              f"workload with the oracle's host-parallel OneSweep port on {threads} threads")
+    best, mean, times, orc, src = _cpu_sort_sample(steps=args.steps, warmup=args.warmup)
+    n = src.size
+    value = n / best / 1e9
     line = {
-        "impl": "reference", "metric": "OneSweep sort throughput, 2^30 uint32 keys-only uniform-random (CPU sample)",
+        "impl": "reference", "metric": METRIC,
         "value": round(value, 4), "unit": "Gkeys/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-        "data": "synthetic (reference InitRandom generator, seed 10, entropy preset 1)",
-        "config": {"workload": f"2^{LOG2_N} uint32 keys-only OneSweep, uniform-random; CPU arm on a 2^{CPU_SAMPLE_LOG2} sample",
+        "ms_per_step": round(best * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": DATA,
+        "config": {"workload": workload(LOG2_N, max(args.gpus, 1)),
+                   "cpu_sample": _sample_text(f"value = best of {args.steps} timed steps"),
+                   "mean_gkeys_s": round(n / mean / 1e9, 4), "ms_per_step_mean": round(mean * 1e3, 3),
                    "note": "the reference has no CPU implementation of this path (SURVEY D2); this is the oracle port"},
-        "cpu_baseline": {"value": round(value, 4), "unit": "Gkeys/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(value, 4), "unit": "Gkeys/s", "cores": HOST_THREADS, "kind": "port",
+                         "sample": _sample_text(f"best of {args.steps} timed steps")},
         "e2e": {"value": round(value, 4), "unit": "Gkeys/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,8 +232,11 @@ def main():
     ap.add_argument("--log2n", type=int, default=LOG2_N, help="keys per GPU (development only; the contract is 30)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip extra_configs (pairs, u64) and ref_cuda (development)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours" and args.warmup < 3:
+        print(f"bench.py: --warmup {args.warmup} raised to 3 (timing rule: W >= 3)", file=sys.stderr)
+        args.warmup = 3
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,14 +282,23 @@ def main():
         pass_ms = result["pass_ms"]
         achieved = ALG_BYTES_PER_KEY_PER_PASS * n / (pass_ms / 1e3) / 1e9
         traffic = ncu_traffic_bytes()
+        # dram read+write bytes of ONE launch of the dominant kernel from the committed `ncu --set full` capture; used
+        # as measured only when the capture was taken at this n, otherwise it is not reported as a measurement
+        traffic_bytes, traffic_note = None, "no ncu capture committed for this kernel yet"
+        if traffic:
+            traffic_note = traffic.get("note", "")
+            if int(traffic.get("log2n", -1)) == args.log2n and "dram_bytes_per_launch" in traffic:
+                traffic_bytes = int(traffic["dram_bytes_per_launch"])
+            else:
+                traffic_note = (f"capture is at 2^{traffic.get('log2n')} (traffic/algorithmic = "
+                                f"{traffic.get('traffic_over_algorithmic')}), not at this n: not reported as measured. " + traffic_note)
         line = {
-            "metric": "OneSweep sort throughput, 2^30 uint32 keys per GPU, keys-only, uniform-random",
+            "metric": METRIC,
             "value": round(value, 3), "unit": "Gkeys/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic (reference InitRandom generator on device, seed 10, entropy preset 1)",
+            "dtype": "u32", "data": DATA,
             "config": {
-                "workload": f"2^{args.log2n} uint32 keys-only OneSweep per GPU, uniform-random (BASELINE.json configs[1])"
-                            + ("" if world == 1 else f"; {world} GPUs: MSD bucket exchange over NVLink then local OneSweep"),
+                "workload": workload(args.log2n, world),
                 "keys_per_gpu": n, "total_keys": total_keys, "passes": 4, "digit_bits": 8,
                 "variant": result["variant"], "tile_keys": result["tile_keys"], "rank_mode": result["rank_mode"],
                 "timing": "CUDA events on the launching stream around each sort, summed over the K steps, max over ranks; "
@@ -265,8 +309,8 @@ def main():
             "roofline": {
                 "bound": "hbm", "kernel": result["kernel"], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4),
-                "traffic": (round(traffic["traffic_over_algorithmic"] * ALG_BYTES_PER_KEY_PER_PASS * n) if traffic else None),
-                "traffic_note": (traffic or {}).get("note", "no ncu capture committed for this kernel yet"),
+                "traffic": traffic_bytes,
+                "traffic_note": traffic_note,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_KEY_PER_PASS * n,
                 "launch_ms": round(pass_ms, 4), "peak_source": peak_src,
                 "kernel_ms": {k: round(v, 4) for k, v in result["kernel_ms"].items()},
@@ -274,17 +318,142 @@ def main():
             "e2e": {"value": round(e2e_value, 3), "unit": "Gkeys/s", "ms_per_step": round(e2e_ms, 3),
                     "steps": result["e2e_steps"], "h2d_bytes_per_step": result["h2d_bytes"],
                     "d2h_bytes_per_step": result["d2h_bytes"],
-                    "api": "osb200_sort_host_keys_u32 (C-ABI, pinned host buffers)"},
+                    "api": result.get("e2e_api", "osb200_sort_host_keys_u32 (C-ABI, pinned host buffers)")},
             "gpu_launches": result["gpu_launches"],
             "clocks": result["clocks"],
             "verified": result["verified"],
         }
+        for k in ("extra_configs", "ref_cuda", "phases_ms"):
+            if k in result:
+                line[k] = result[k]
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def multiset_checksum(t):
+    """Order-independent checksum of a device tensor's 32-bit words (sum and a mixed sum, mod 2^64), chunked."""
+    import torch
+
+    a = b = 0
+    flat = t.view(torch.int32)
+    step = 1 << 27
+    for i in range(0, flat.numel(), step):
+        x = flat[i:i + step].to(torch.int64) & 0xFFFFFFFF
+        a += int(x.sum().item())
+        b += int(((x * 2654435761) ^ (x >> 7)).sum().item())
+    m = (1 << 64) - 1
+    return a & m, b & m
+
+
+def _time_sorts(steps, warmup, restore, sort, stream):
+    """K device-timed sorts (CUDA events on the launching stream around each sort; restore() is untimed)."""
+    import torch
+
+    for _ in range(warmup):
+        restore()
+        sort()
+    torch.cuda.synchronize()
+    ev = []
+    for _ in range(steps):
+        restore()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        sort()
+        b.record(stream)
+        ev.append((a, b))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev) / steps
+
+
+def extra_config_pairs(g, n, peak, steps=5, warmup=3):
+    """BASELINE.json configs[2]: 2^30 (uint32 key, uint32 payload) pairs, device-timed, with its own roofline."""
+    import numpy as np
+    import torch
+
+    k0 = torch.empty(n, dtype=torch.int32, device="cuda")
+    v0 = torch.empty(n, dtype=torch.int32, device="cuda")
+    g.init_random(k0, 0, SEED, payload=v0, payload_is_index=True)
+    k, v = torch.empty_like(k0), torch.empty_like(v0)
+    s = g.OneSweepSorter(n, 4, 4)
+    s.set_option("profile", 1)
+    stream = torch.cuda.current_stream()
+    ck = multiset_checksum(k0)
+    ms = _time_sorts(steps, warmup, lambda: (k.copy_(k0), v.copy_(v0)), lambda: s.sort_pairs(k, v), stream)
+    prof = s.last_profile()
+    pass_ms = float(np.mean(prof[2:]))
+    ok = s.validate(k) == 0 and multiset_checksum(k) == ck
+    # payload round trip on a slice: output key i is the input key at index v[i]
+    idx = v[: 1 << 22].to(torch.int64) & 0xFFFFFFFF
+    ok = ok and bool(torch.equal(k0[idx], k[: 1 << 22]))
+    s.close()
+    del k0, v0, k, v, idx
+    torch.cuda.empty_cache()
+    ach = 16 * n / (pass_ms / 1e3) / 1e9
+    return {"workload": f"2^{n.bit_length() - 1} (uint32 key, uint32 payload) pairs, uniform-random keys, payload = index (BASELINE.json configs[2])",
+            "value": round(n / (ms / 1e3) / 1e9, 3), "unit": "Gpairs/s", "ms_per_step": round(ms, 4), "steps": steps, "warmup": warmup,
+            "passes": 4, "pct_of_peak_64B_per_pair": round(64.0 * n / (ms / 1e3) / 1e9 / peak * 100, 2),
+            "roofline": {"bound": "hbm", "kernel": "digit_binning_wide_kernel<u32, pairs>", "achieved": round(ach, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(ach / peak, 4), "algorithmic_bytes_per_launch": 16 * n, "launch_ms": round(pass_ms, 4)},
+            "kernel_ms": {"global_histogram": round(prof[0], 4), "digit_binning_pass_mean": round(pass_ms, 4)}, "verified": bool(ok)}
+
+
+def extra_config_u64(g, n, peak, steps=5, warmup=3):
+    """BASELINE.json configs[3]: 2^30 uint64 keys-only (8 digit passes), device-timed, with its own roofline."""
+    import numpy as np
+    import torch
+
+    w0 = torch.empty(2 * n, dtype=torch.int32, device="cuda")
+    g.init_random(w0, 0, SEED)  # hi/lo words are consecutive draws of the reference generator
+    k0 = w0.view(torch.int64)
+    k = torch.empty_like(k0)
+    s = g.OneSweepSorter(n, 8, 0)
+    s.set_option("profile", 1)
+    stream = torch.cuda.current_stream()
+    ck = multiset_checksum(k0)
+    ms = _time_sorts(steps, warmup, lambda: k.copy_(k0), lambda: s.sort_keys(k), stream)
+    prof = s.last_profile()
+    pass_ms = float(np.mean(prof[2:]))
+    ok = s.validate(k) == 0 and multiset_checksum(k) == ck
+    s.close()
+    del w0, k0, k
+    torch.cuda.empty_cache()
+    ach = 16 * n / (pass_ms / 1e3) / 1e9
+    return {"workload": f"2^{n.bit_length() - 1} uint64 keys-only, uniform-random, 8 digit passes (BASELINE.json configs[3])",
+            "value": round(n / (ms / 1e3) / 1e9, 3), "unit": "Gkeys/s", "ms_per_step": round(ms, 4), "steps": steps, "warmup": warmup,
+            "passes": 8, "pct_of_peak_128B_per_key": round(128.0 * n / (ms / 1e3) / 1e9 / peak * 100, 2),
+            "roofline": {"bound": "hbm", "kernel": "digit_binning_wide_kernel<u64>", "achieved": round(ach, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(ach / peak, 4), "algorithmic_bytes_per_launch": 16 * n, "launch_ms": round(pass_ms, 4)},
+            "kernel_ms": {"global_histogram": round(prof[0], 4), "digit_binning_pass_mean": round(pass_ms, 4)}, "verified": bool(ok)}
+
+
+def ref_cuda_leg(n):
+    """The reference's own CUDA OneSweep kernels (oracle/_ref, compiled for sm_100a from /root/reference) timed in this
+    process on this GPU with the reference's protocol (OneSweepDispatcher.cuh:193-239: InitRandom(seed+i) per iteration,
+    cudaEvent around the dispatch incl. its memsets, iteration 0 discarded).  A measured comparator only."""
+    import torch
+    from tests import oraclelib
+
+    ref = oraclelib.load_ref()
+    if ref is None:
+        return {"unavailable": "oracle/_ref/libref_onesweep.so not built"}
+    out = {"what": "b0nes164/GPUSorting GPUSortingCUDA OneSweep kernels, unmodified but for the SURVEY D4 pragma token, sm_100a build, "
+                   "timed with the reference's BatchTimingKeysOnly protocol", "unit": "Gkeys/s"}
+    for e, iters in ((28, 20), (n.bit_length() - 1, 5)):
+        m = 1 << e
+        h = ref.lib.ref_create(m)
+        a, alt = torch.empty(m, dtype=torch.int32, device="cuda"), torch.empty(m, dtype=torch.int32, device="cuda")
+        total_ms = float(ref.lib.ref_batch_timing_keys(h, a.data_ptr(), alt.data_ptr(), m, iters, SEED))
+        bad = int(ref.lib.ref_validate_keys(h, a.data_ptr(), m))
+        ref.lib.ref_destroy(h)
+        del a, alt
+        torch.cuda.empty_cache()
+        out[f"keys_2pow{e}"] = {"value": round(m * iters / (total_ms / 1e3) / 1e9, 3), "ms_per_sort": round(total_ms / iters, 4),
+                                "iters": iters, "sorted": bad == 0}
+    return out
 
 
 def bench_single(args, g, n, device_index):
@@ -299,6 +468,7 @@ def bench_single(args, g, n, device_index):
     s.set_option("variant", variant)
     s.set_option("profile", 1)
     stream = torch.cuda.current_stream()
+    checksum_in = multiset_checksum(src)
 
     def one_step(timed):
         work.copy_(src)  # restore the unsorted input (untimed)
@@ -326,14 +496,17 @@ def bench_single(args, g, n, device_index):
                  "digit_binning_pass_mean": float(prof[:, 2:].mean())}
     for p in range(prof.shape[1] - 2):
         kernel_ms[f"digit_binning_pass_{p}"] = float(prof[:, 2 + p].mean())
-    verified = s.validate(work) == 0
+    # sorted (the reference's Validate) AND the same multiset as the input (an output of equal keys would not pass)
+    verified = s.validate(work) == 0 and multiset_checksum(work) == checksum_in
+    launches = s.info("launches_per_sort")
 
     # ---- end to end through the C-ABI host entry point, pinned host memory ---------------------------------
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     host_src = torch.empty(n, dtype=torch.int32).pin_memory()
     host_src.copy_(src)
     host_work = torch.empty(n, dtype=torch.int32).pin_memory()
-    del src
+    del src, work
+    torch.cuda.empty_cache()
     total = 0.0
     for i in range(e2e_steps + 1):
         host_work.copy_(host_src)  # untimed restore
@@ -346,14 +519,22 @@ def bench_single(args, g, n, device_index):
     e2e_ms = total / e2e_steps * 1e3
     hw = host_work.numpy().view(np.uint32)
     verified = verified and bool((hw[:-1][:: 4097] <= hw[1:][:: 4097]).all())
+    verified = verified and int(hw.sum(dtype=np.uint64)) == checksum_in[0]
+    tile_keys, rank_mode = s.info("tile_keys"), s.info("rank_mode")
+    s.close()
+    del host_src, host_work, hw
+    torch.cuda.empty_cache()
     out = {
         "ms_per_step": ms, "pass_ms": kernel_ms["digit_binning_pass_mean"], "kernel_ms": kernel_ms,
         "kernel": "digit_binning_wide_kernel" if variant == 2 else ("digit_binning_persistent_kernel" if variant == 1 else "digit_binning_tile_kernel"),
-        "variant": variant, "tile_keys": s.info("tile_keys"), "rank_mode": "atomic" if s.info("rank_mode") == 0 else "ballot",
+        "variant": variant, "tile_keys": tile_keys, "rank_mode": "atomic" if rank_mode == 0 else "ballot",
         "e2e_ms_per_step": e2e_ms, "e2e_steps": e2e_steps, "h2d_bytes": 4 * n, "d2h_bytes": 4 * n,
-        "gpu_launches": args.steps * s.info("launches_per_sort"), "clocks": clocks, "verified": verified,
+        "gpu_launches": args.steps * launches, "clocks": clocks, "verified": verified,
     }
-    s.close()
+    if not args.no_extra:
+        peak, _ = measured_peak_gbs()
+        out["extra_configs"] = [extra_config_pairs(g, n, peak), extra_config_u64(g, n, peak)]
+        out["ref_cuda"] = ref_cuda_leg(n)
     return out
 
 

@@ -115,7 +115,8 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
     if (n <= 1) return OSB200_OK;
     if (n > s->max_n) return OSB200_ERR_SIZE;
     if (!d_keys || (reinterpret_cast<uintptr_t>(d_keys) & 15u)) return OSB200_ERR_INVALID_ARG;
-    if (s->value_bytes && !d_vals) return OSB200_ERR_INVALID_ARG;
+    // d_vals == nullptr is a keys-only sort (also on a pairs-capable handle); the handle is never modified to say so
+    if (d_vals && !s->value_bytes) return OSB200_ERR_INVALID_ARG;
     const int places = s->key_bytes;
 
     OSB_TRY(cudaMemsetAsync(s->control, 0, ControlLayout::zeroed_bytes, stream));
@@ -177,16 +178,16 @@ int sort_host_impl(osb200_sorter* s, void* h_keys, uint32_t* h_vals, uint64_t n)
 {
     if (n <= 1) return OSB200_OK;
     if (n > s->max_n) return OSB200_ERR_SIZE;
-    if (!h_keys || (s->value_bytes && !h_vals)) return OSB200_ERR_INVALID_ARG;
+    if (!h_keys || (h_vals && !s->value_bytes)) return OSB200_ERR_INVALID_ARG;
     int st = ensure_staging(s);
     if (st != OSB200_OK) return st;
     cudaStream_t q = s->own_stream;
     OSB_TRY(cudaMemcpyAsync(s->stage_keys, h_keys, n * s->key_bytes, cudaMemcpyHostToDevice, q));
-    if (s->value_bytes) OSB_TRY(cudaMemcpyAsync(s->stage_vals, h_vals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, q));
-    st = sort_impl(s, s->stage_keys, s->value_bytes ? s->stage_vals : nullptr, n, q);
+    if (h_vals) OSB_TRY(cudaMemcpyAsync(s->stage_vals, h_vals, n * sizeof(uint32_t), cudaMemcpyHostToDevice, q));
+    st = sort_impl(s, s->stage_keys, h_vals ? s->stage_vals : nullptr, n, q);
     if (st != OSB200_OK) return st;
     OSB_TRY(cudaMemcpyAsync(h_keys, s->stage_keys, n * s->key_bytes, cudaMemcpyDeviceToHost, q));
-    if (s->value_bytes) OSB_TRY(cudaMemcpyAsync(h_vals, s->stage_vals, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, q));
+    if (h_vals) OSB_TRY(cudaMemcpyAsync(h_vals, s->stage_vals, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, q));
     OSB_TRY(cudaStreamSynchronize(q));
     return OSB200_OK;
 }
@@ -321,12 +322,7 @@ int osb200_destroy(osb200_handle h)
 int osb200_sort_keys_u32(osb200_handle h, uint32_t* d_keys, uint64_t n, void* stream)
 {
     if (check_handle(h) != OSB200_OK || h->key_bytes != 4) return OSB200_ERR_INVALID_ARG;
-    // a pairs-capable sorter may sort keys only
-    const int vb = h->value_bytes;
-    h->value_bytes = 0;
-    const int st = sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream));
-    h->value_bytes = vb;
-    return st;
+    return sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream));  // a pairs-capable sorter may sort keys only
 }
 
 int osb200_sort_pairs_u32(osb200_handle h, uint32_t* d_keys, uint32_t* d_values, uint64_t n, void* stream)
@@ -369,11 +365,7 @@ int osb200_sort_keys_typed(osb200_handle h, void* d_keys, uint64_t n, int key_ty
     if (st != OSB200_OK) return st;
     if (h->cfg.variant != osb::kVariantWide) return OSB200_ERR_UNSUPPORTED;
     const bool plain = c.a == 0 && c.b == 0 && c.d == 0;
-    const int vb = h->value_bytes;
-    h->value_bytes = 0;
-    st = sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream), plain ? nullptr : &c);
-    h->value_bytes = vb;
-    return st;
+    return sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream), plain ? nullptr : &c);
 }
 
 int osb200_sort_pairs_typed(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int key_type, int descending,
@@ -392,16 +384,13 @@ int osb200_sort_pairs_typed(osb200_handle h, void* d_keys, uint32_t* d_values, u
 int osb200_sort_host_keys_u32(osb200_handle h, uint32_t* h_keys, uint64_t n)
 {
     if (check_handle(h) != OSB200_OK || h->key_bytes != 4) return OSB200_ERR_INVALID_ARG;
-    const int vb = h->value_bytes;
-    h->value_bytes = 0;
-    const int st = sort_host_impl(h, h_keys, nullptr, n);
-    h->value_bytes = vb;
-    return st;
+    return sort_host_impl(h, h_keys, nullptr, n);
 }
 
 int osb200_sort_host_pairs_u32(osb200_handle h, uint32_t* h_keys, uint32_t* h_values, uint64_t n)
 {
     if (check_handle(h) != OSB200_OK || h->key_bytes != 4 || h->value_bytes != 4) return OSB200_ERR_INVALID_ARG;
+    if (n > 1 && !h_values) return OSB200_ERR_INVALID_ARG;
     return sort_host_impl(h, h_keys, h_values, n);
 }
 

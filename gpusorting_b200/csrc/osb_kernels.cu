@@ -537,6 +537,8 @@ lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint
 // OSB_EXP: compile-time experiments for tools/sweep.sh, OFF (0) in the product build.  Not yet measured on hardware:
 //   bit 0 (1): 32-bit element offsets per digit instead of 64-bit byte pointers in the scatter (valid for n <= 2^32, out != 0)
 //   bit 1 (2): 256-bin passes store run by run, warp-owned digits, in chunks aligned to the destination's 128-byte lines
+//   bit 2 (4): the chained-scan lookback runs BEFORE the rank phase (digit warps look back while the other warps rank)
+//   bit 3 (8): full tiles are staged by ONE TMA bulk copy (cp.async.bulk + mbarrier) into the sorted-tile buffer, then LDS
 #ifndef OSB_EXP
 #define OSB_EXP 0
 #endif
@@ -559,6 +561,7 @@ struct WideSmem {
 #endif
     uint32_t wtot[kRadix / 32];
     uint32_t tile;
+    alignas(8) uint64_t bar;                         // (TMA tile load) "tile landed" mbarrier
 };
 
 
@@ -584,7 +587,18 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
         uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
         for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
     }
-    if (tid == 0) sm.tile = atomicAdd(ticket, 1u);  // dynamic tile id: predecessors are already scheduled
+    if (tid == 0) {
+        const uint32_t t = atomicAdd(ticket, 1u);  // dynamic tile id: predecessors are already scheduled
+        sm.tile = t;
+#if OSB_EXP & 8
+        mbar_init(&sm.bar, 1);
+        fence_mbar_init();
+        if (static_cast<uint64_t>(t) * T + T <= n) {
+            mbar_expect_tx(&sm.bar, T * sizeof(KeyT));
+            tma_load_1d(sm.sorted, in + static_cast<uint64_t>(t) * T, T * sizeof(KeyT), &sm.bar);
+        }
+#endif
+    }
     __syncthreads();
     const uint32_t tile = sm.tile;
     const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
@@ -596,8 +610,14 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     uint32_t val[PAIRS ? K : 1];
     const uint32_t warp_off = warp * (32 * K) + lane;
     if (full) {
+#if OSB_EXP & 8
+        mbar_wait(&sm.bar, 0);
+#pragma unroll
+        for (int i = 0; i < K; ++i) key[i] = sm.sorted[warp_off + i * 32];
+#else
 #pragma unroll
         for (int i = 0; i < K; ++i) key[i] = ld_stream(in + tile_base + warp_off + i * 32);
+#endif
         if constexpr (PAIRS) {
 #pragma unroll
             for (int i = 0; i < K; ++i) val[i] = ld_stream(in_val + tile_base + warp_off + i * 32);
@@ -643,16 +663,7 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     }
     __syncthreads();
 
-    // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -----------------
-    // (typed keys: the last pass stores the keys decoded; the digit was taken from the encoded key, and the scatter
-    // below re-derives it from the tile, so the decoded form is produced only at the very end, in the store)
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
-        sm.sorted[slot] = key[i];
-        if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
-    }
-
+#if OSB_EXP & 4
     // ---- chained scan with decoupled lookback ------------------------------------------------------------
     if (tid < kRadix) {
         const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch);
@@ -675,6 +686,41 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
         sm.off32[tid] = static_cast<uint32_t>(first);
 #endif
     }
+#endif
+    // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -----------------
+    // (typed keys: the last pass stores the keys decoded; the digit was taken from the encoded key, and the scatter
+    // below re-derives it from the tile, so the decoded form is produced only at the very end, in the store)
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
+        sm.sorted[slot] = key[i];
+        if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
+    }
+
+#if !(OSB_EXP & 4)
+    // ---- chained scan with decoupled lookback ------------------------------------------------------------
+    if (tid < kRadix) {
+        const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch);
+        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
+                           desc_pack(epoch, kFlagInclusive, prior + tile_count));
+        const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
+        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
+        if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
+        if (tid < 32 || (OSB_EXP & 2)) {
+            // the all-ones padding of the ragged last tile sits at the end of the run of its digit: not live
+            const uint32_t pad_digit = digit_of(static_cast<KeyT>(~static_cast<KeyT>(0)), shift);
+            const uint32_t live = tile_count - ((tid == pad_digit && !full) ? (T - valid) : 0u);
+            sm.run[tid] = tile_excl | (live << 16);
+#if OSB_EXP & 2
+            const uint32_t lm = __ballot_sync(0xffffffffu, live > 1024u);
+            if (lane == 0) sm.longmask[warp] = lm;
+#endif
+        }
+#if OSB_EXP & 1
+        sm.off32[tid] = static_cast<uint32_t>(first);
+#endif
+    }
+#endif
     __syncthreads();
 
     // ---- scatter -----------------------------------------------------------------------------------------

@@ -314,7 +314,11 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
     }
     h->last_bins = bins;
     const uint64_t mine = recv_count[h->rank];
-    if (mine > h->capacity) return OSB200_ERR_SIZE;  // bucket imbalance beyond the slack chosen at create
+    // Bucket imbalance beyond the slack chosen at create.  Every rank holds the whole recv_count[] and the same capacity
+    // (max_n_local and slack_percent must be identical on all ranks), so ALL ranks take this exit together, before any
+    // collective or peer store of the exchange: nobody is left waiting in a barrier for a rank that bailed out.
+    for (int r = 0; r < R; ++r)
+        if (recv_count[r] > h->capacity) return OSB200_ERR_SIZE;
     OSB_TRY(cudaEventRecord(h->ev[1], q));
 
     // 4. exchange

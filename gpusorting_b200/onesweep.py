@@ -23,8 +23,12 @@ from ._lib import check, lib
 
 ENTROPY_PRESET_1, ENTROPY_PRESET_2, ENTROPY_PRESET_3, ENTROPY_PRESET_4, ENTROPY_PRESET_5 = range(5)
 
-_KEY_DTYPES_4 = (torch.int32, torch.uint32, torch.float32)
-_KEY_DTYPES_8 = (torch.int64, torch.uint64, torch.float64)
+# sort_keys / sort_pairs order keys by their UNSIGNED bit pattern: only integer containers are accepted there (a float
+# tensor would silently sort negatives wrongly).  Float tensors go through sort_*_typed, which states the key type.
+_KEY_DTYPES_4 = (torch.int32, torch.uint32)
+_KEY_DTYPES_8 = (torch.int64, torch.uint64)
+_TYPED_DTYPES_4 = (torch.int32, torch.uint32, torch.float32)
+_TYPED_DTYPES_8 = (torch.int64, torch.uint64, torch.float64)
 KEY_TYPES = {"u32": 0, "i32": 1, "f32": 2, "u64": 3, "i64": 4, "f64": 5}
 
 
@@ -33,9 +37,13 @@ def _stream_ptr(stream: Optional[torch.cuda.Stream]) -> int:
     return int(s.cuda_stream)
 
 
-def _check_dev_tensor(t: torch.Tensor, dtypes, name: str) -> None:
+def _check_dev_tensor(t: torch.Tensor, dtypes, name: str, n: Optional[int] = None, device: Optional[int] = None) -> None:
     if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous() and t.dtype in dtypes and t.dim() == 1):
         raise TypeError(f"{name} must be a contiguous 1-D CUDA tensor with dtype in {dtypes}")
+    if device is not None and t.device.index != device:
+        raise ValueError(f"{name} lives on cuda:{t.device.index}, the sorter on cuda:{device}")
+    if n is not None and not (0 <= n <= t.numel()):
+        raise ValueError(f"n={n} is outside 0..{name}.numel()={t.numel()}")
 
 
 class OneSweepSorter:
@@ -92,14 +100,21 @@ class OneSweepSorter:
         return [float(buf[i]) for i in range(k)]
 
     # -- device sorts -------------------------------------------------------------------------------
+    # Every entry point validates dtype / device / contiguity / n against the tensors it is handed and makes the
+    # sorter's device current for the launch (the C side launches on the current device).
+    def _raw(self):
+        return _KEY_DTYPES_4 if self.key_bytes == 4 else _KEY_DTYPES_8
+
+    def _typed(self):
+        return _TYPED_DTYPES_4 if self.key_bytes == 4 else _TYPED_DTYPES_8
+
     def sort_keys(self, keys: torch.Tensor, n: Optional[int] = None, stream=None) -> torch.Tensor:
         n = keys.numel() if n is None else int(n)
-        if self.key_bytes == 4:
-            _check_dev_tensor(keys, _KEY_DTYPES_4, "keys")
-            check(lib.osb200_sort_keys_u32(self._h, keys.data_ptr(), n, _stream_ptr(stream)), "osb200_sort_keys_u32")
-        else:
-            _check_dev_tensor(keys, _KEY_DTYPES_8, "keys")
-            check(lib.osb200_sort_keys_u64(self._h, keys.data_ptr(), n, _stream_ptr(stream)), "osb200_sort_keys_u64")
+        _check_dev_tensor(keys, self._raw(), "keys", n, self.device)
+        fn, what = ((lib.osb200_sort_keys_u32, "osb200_sort_keys_u32") if self.key_bytes == 4
+                    else (lib.osb200_sort_keys_u64, "osb200_sort_keys_u64"))
+        with torch.cuda.device(self.device):
+            check(fn(self._h, keys.data_ptr(), n, _stream_ptr(stream)), what)
         return keys
 
     def sort_keys_typed(self, keys: torch.Tensor, key_type: str, descending: bool = False, n: Optional[int] = None,
@@ -107,28 +122,29 @@ class OneSweepSorter:
         """Signed / float keys and descending order (reference HLSL: SortCommon.hlsl:134-154,594-656).  key_type in
         KEY_TYPES; it states how the bits are ordered, whatever the tensor dtype (which only has to have the width)."""
         n = keys.numel() if n is None else int(n)
-        _check_dev_tensor(keys, _KEY_DTYPES_4 if self.key_bytes == 4 else _KEY_DTYPES_8, "keys")
-        check(lib.osb200_sort_keys_typed(self._h, keys.data_ptr(), n, KEY_TYPES[key_type], 1 if descending else 0,
-                                         _stream_ptr(stream)), "osb200_sort_keys_typed")
+        _check_dev_tensor(keys, self._typed(), "keys", n, self.device)
+        with torch.cuda.device(self.device):
+            check(lib.osb200_sort_keys_typed(self._h, keys.data_ptr(), n, KEY_TYPES[key_type], 1 if descending else 0,
+                                             _stream_ptr(stream)), "osb200_sort_keys_typed")
         return keys
 
     def sort_pairs_typed(self, keys: torch.Tensor, values: torch.Tensor, key_type: str, descending: bool = False,
                          n: Optional[int] = None, stream=None):
         n = keys.numel() if n is None else int(n)
-        _check_dev_tensor(keys, _KEY_DTYPES_4, "keys")
-        _check_dev_tensor(values, _KEY_DTYPES_4, "values")
-        check(lib.osb200_sort_pairs_typed(self._h, keys.data_ptr(), values.data_ptr(), n, KEY_TYPES[key_type],
-                                          1 if descending else 0, _stream_ptr(stream)), "osb200_sort_pairs_typed")
+        _check_dev_tensor(keys, _TYPED_DTYPES_4, "keys", n, self.device)
+        _check_dev_tensor(values, _TYPED_DTYPES_4, "values", n, self.device)
+        with torch.cuda.device(self.device):
+            check(lib.osb200_sort_pairs_typed(self._h, keys.data_ptr(), values.data_ptr(), n, KEY_TYPES[key_type],
+                                              1 if descending else 0, _stream_ptr(stream)), "osb200_sort_pairs_typed")
         return keys, values
 
     def sort_pairs(self, keys: torch.Tensor, values: torch.Tensor, n: Optional[int] = None, stream=None):
         n = keys.numel() if n is None else int(n)
-        _check_dev_tensor(keys, _KEY_DTYPES_4, "keys")
-        _check_dev_tensor(values, _KEY_DTYPES_4, "values")
-        if values.numel() < n:
-            raise ValueError("values shorter than n")
-        check(lib.osb200_sort_pairs_u32(self._h, keys.data_ptr(), values.data_ptr(), n, _stream_ptr(stream)),
-              "osb200_sort_pairs_u32")
+        _check_dev_tensor(keys, _KEY_DTYPES_4, "keys", n, self.device)
+        _check_dev_tensor(values, _TYPED_DTYPES_4, "values", n, self.device)  # payloads are opaque 32-bit words
+        with torch.cuda.device(self.device):
+            check(lib.osb200_sort_pairs_u32(self._h, keys.data_ptr(), values.data_ptr(), n, _stream_ptr(stream)),
+                  "osb200_sort_pairs_u32")
         return keys, values
 
     # -- host-buffer sorts (end-to-end: H2D + sort + D2H inside the call) ---------------------------
@@ -151,24 +167,36 @@ class OneSweepSorter:
     # -- kernel-level entry points (parity tests) ---------------------------------------------------
     def global_histogram(self, keys: torch.Tensor, n: Optional[int] = None, stream=None) -> torch.Tensor:
         n = keys.numel() if n is None else int(n)
+        _check_dev_tensor(keys, self._typed(), "keys", n, self.device)
         hist = torch.empty(self.key_bytes * 256, dtype=torch.int64, device=keys.device)
-        check(lib.osb200_global_histogram(self._h, keys.data_ptr(), n, hist.data_ptr(), _stream_ptr(stream)),
-              "osb200_global_histogram")
+        with torch.cuda.device(self.device):
+            check(lib.osb200_global_histogram(self._h, keys.data_ptr(), n, hist.data_ptr(), _stream_ptr(stream)),
+                  "osb200_global_histogram")
         return hist.view(self.key_bytes, 256)
 
     def digit_binning_pass(self, src: torch.Tensor, dst: torch.Tensor, radix_shift: int, src_values=None,
                            dst_values=None, n: Optional[int] = None, stream=None) -> None:
         n = src.numel() if n is None else int(n)
+        _check_dev_tensor(src, self._typed(), "src", n, self.device)
+        _check_dev_tensor(dst, self._typed(), "dst", n, self.device)
+        if (src_values is None) != (dst_values is None):
+            raise ValueError("src_values and dst_values go together")
+        if src_values is not None:
+            _check_dev_tensor(src_values, _TYPED_DTYPES_4, "src_values", n, self.device)
+            _check_dev_tensor(dst_values, _TYPED_DTYPES_4, "dst_values", n, self.device)
         sv = src_values.data_ptr() if src_values is not None else None
         dv = dst_values.data_ptr() if dst_values is not None else None
-        check(lib.osb200_digit_binning_pass(self._h, src.data_ptr(), dst.data_ptr(), sv, dv, n, int(radix_shift),
-                                            _stream_ptr(stream)), "osb200_digit_binning_pass")
+        with torch.cuda.device(self.device):
+            check(lib.osb200_digit_binning_pass(self._h, src.data_ptr(), dst.data_ptr(), sv, dv, n, int(radix_shift),
+                                                _stream_ptr(stream)), "osb200_digit_binning_pass")
 
     def validate(self, keys: torch.Tensor, n: Optional[int] = None, stream=None) -> int:
         """Number of adjacent inversions (reference Validate, UtilityKernels.cuh:403-429); 0 == sorted."""
         n = keys.numel() if n is None else int(n)
+        _check_dev_tensor(keys, self._typed(), "keys", n, self.device)
         err = ctypes.c_uint64(0)
-        check(lib.osb200_validate(self._h, keys.data_ptr(), n, ctypes.byref(err), _stream_ptr(stream)), "osb200_validate")
+        with torch.cuda.device(self.device):
+            check(lib.osb200_validate(self._h, keys.data_ptr(), n, ctypes.byref(err), _stream_ptr(stream)), "osb200_validate")
         return int(err.value)
 
 
@@ -188,7 +216,9 @@ def init_random(keys: torch.Tensor, and_count: int, seed: int, n: Optional[int] 
                 payload: Optional[torch.Tensor] = None, payload_is_index: bool = False, stream=None) -> None:
     """The reference's input generator InitRandom<<<256,256>>> (UtilityKernels.cuh:53-117), on the device."""
     n = keys.numel() if n is None else int(n)
-    _check_dev_tensor(keys, _KEY_DTYPES_4, "keys")
+    _check_dev_tensor(keys, _TYPED_DTYPES_4, "keys", n)
+    if payload is not None:
+        _check_dev_tensor(payload, _TYPED_DTYPES_4, "payload", n, keys.device.index)
     pp = payload.data_ptr() if payload is not None else None
     check(lib.osb200_init_random_u32(keys.data_ptr(), pp, n, int(and_count), int(seed) & 0xFFFFFFFF,
                                      1 if payload_is_index else 0, _stream_ptr(stream)), "osb200_init_random_u32")
@@ -201,8 +231,9 @@ def init_random(keys: torch.Tensor, and_count: int, seed: int, n: Optional[int] 
 _CACHE: dict = {}
 
 
-def _cached_sorter(device: int, key_bytes: int, value_bytes: int, n: int) -> OneSweepSorter:
-    k = (device, key_bytes, value_bytes)
+def _cached_sorter(device: int, key_bytes: int, value_bytes: int, n: int, stream_ptr: int) -> OneSweepSorter:
+    # one handle per stream: the ABI allows one sort in flight per handle, and sorts on one stream are ordered
+    k = (device, key_bytes, value_bytes, stream_ptr)
     s = _CACHE.get(k)
     if s is None or s.max_n < n:
         if s is not None:
@@ -216,7 +247,11 @@ def Sort(keys: torch.Tensor, values: Optional[torch.Tensor] = None, n: Optional[
     """OneSweep::Sort(keys[, values], n): ascending, stable, in place; returns its arguments."""
     n = keys.numel() if n is None else int(n)
     kb = keys.element_size()
-    s = _cached_sorter(keys.device.index, kb, 0 if values is None else 4, n)
+    if not (isinstance(keys, torch.Tensor) and keys.is_cuda):
+        raise TypeError("keys must be a CUDA tensor")
+    with torch.cuda.device(keys.device.index):
+        sp = _stream_ptr(stream)
+    s = _cached_sorter(keys.device.index, kb, 0 if values is None else 4, n, sp)
     if values is None:
         return s.sort_keys(keys, n, stream)
     return s.sort_pairs(keys, values, n, stream)

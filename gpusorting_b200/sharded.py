@@ -87,10 +87,33 @@ class ShardedSorter:
         for hh in (a, b):
             check(lib.osb200_set_option(hh, key.encode(), int(value)), f"osb200_set_option({key})")
 
+    def local_profile(self):
+        """Per-kernel ms of the last LOCAL OneSweep on this rank ([hist, scan, pass0..3]) when option 'profile' was set
+        through set_local_option: the local handle's own CUDA events, not an estimate."""
+        a, b = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib.osb200_sharded_local_handle(self._h, ctypes.byref(a), ctypes.byref(b)), "osb200_sharded_local_handle")
+        buf = (ctypes.c_float * 16)()
+        k = lib.osb200_get_profile(b, buf, 16)
+        if k < 0:
+            check(k, "osb200_get_profile")
+        return [float(buf[i]) for i in range(k)]
+
+    def local_info(self, key: str) -> int:
+        a, b = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib.osb200_sharded_local_handle(self._h, ctypes.byref(a), ctypes.byref(b)), "osb200_sharded_local_handle")
+        return int(lib.osb200_get_info(b, key.encode()))
+
     def sort_keys(self, keys: torch.Tensor, n_local: Optional[int] = None, stream=None) -> torch.Tensor:
         """keys: this rank's unsorted int32/uint32 CUDA tensor (not modified).  Returns this rank's slice of the global
         ascending order as a tensor that aliases sorter-owned memory (valid until the next call)."""
         n_local = keys.numel() if n_local is None else int(n_local)
+        if not (isinstance(keys, torch.Tensor) and keys.is_cuda and keys.is_contiguous() and keys.dim() == 1
+                and keys.dtype in (torch.int32, torch.uint32)):
+            raise TypeError("keys must be a contiguous 1-D int32/uint32 CUDA tensor")
+        if keys.device.index != torch.cuda.current_device():
+            raise ValueError("keys must live on this rank's current CUDA device")
+        if not (0 <= n_local <= keys.numel()):
+            raise ValueError(f"n_local={n_local} is outside 0..keys.numel()={keys.numel()}")
         s = stream if stream is not None else torch.cuda.current_stream()
         out, n_out = ctypes.c_void_p(), ctypes.c_uint64(0)
         check(lib.osb200_sharded_sort_keys_u32(self._h, keys.data_ptr(), n_local, ctypes.byref(out), ctypes.byref(n_out),
@@ -142,6 +165,20 @@ def verify_global_order(res: torch.Tensor, rank: int, world: int) -> bool:
     return ok
 
 
+def global_multiset_checksum(t: torch.Tensor) -> tuple:
+    """Order-independent checksum (sum and a mixed sum of the 32-bit words, mod 2^63) all-reduced over the ranks: equal
+    before and after a sharded sort iff no key was lost, duplicated or replaced (up to hash collisions)."""
+    a = torch.zeros(2, dtype=torch.int64, device="cuda")
+    flat = t.view(torch.int32)
+    step = 1 << 27
+    for i in range(0, flat.numel(), step):
+        x = flat[i:i + step].to(torch.int64) & 0xFFFFFFFF
+        a[0] += x.sum()
+        a[1] += ((x * 2654435761) ^ (x >> 7)).sum()
+    dist.all_reduce(a)  # int64 wrap-around is still a function of the multiset only
+    return int(a[0]), int(a[1])
+
+
 def bench_sharded(args, rank: int, world: int, local_rank: int, n: int):
     """bench.py body for N>1: weak scaling, 2^30 keys per rank (seed 10+rank), sharded sort timed on the device."""
     import os
@@ -156,8 +193,10 @@ def bench_sharded(args, rank: int, world: int, local_rank: int, n: int):
     s = ShardedSorter(n, slack_percent=int(os.environ.get("OSB_SLACK", "12")))
     if os.environ.get("OSB_FUSED") is not None:
         s.set_fused(os.environ["OSB_FUSED"] != "0")
+    s.set_local_option("profile", 1)
     total_in = torch.tensor([n], dtype=torch.int64, device="cuda")
     dist.all_reduce(total_in)
+    checksum_in = global_multiset_checksum(src)
     stream = torch.cuda.current_stream()
 
     def one_step():
@@ -174,18 +213,20 @@ def bench_sharded(args, rank: int, world: int, local_rank: int, n: int):
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize()
-    events, phases = [], []
+    events, phases, local_prof = [], [], []
     for _ in range(args.steps):
         a, b, res = one_step()
         events.append((a, b))
         phases.append(s.last_timing())
+        local_prof.append(s.local_profile())
     torch.cuda.synchronize()
     dist.barrier()
     clocks = sampler.result()
     ms = sum(a.elapsed_time(b) for a, b in events) / args.steps
     total_out = torch.tensor([res.numel()], dtype=torch.int64, device="cuda")
     dist.all_reduce(total_out)
-    verified = verify_global_order(res, rank, world) and int(total_out) == int(total_in)
+    verified = (verify_global_order(res, rank, world) and int(total_out) == int(total_in)
+                and global_multiset_checksum(res) == checksum_in)
     ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
 
     # end to end: pinned host keys in, sorted slice back out
@@ -202,12 +243,21 @@ def bench_sharded(args, rank: int, world: int, local_rank: int, n: int):
         if i:
             tot += dt
     e2e_ms = tot / e2e_steps * 1e3
-    local_pass_ms = ph["local_sort_ms"] / 4.6  # ~ (4 passes + histogram) share; detailed split printed below
+    # the local sort's DigitBinningPass time: this rank's local handle recorded CUDA events between its kernels
+    lp = np.array(local_prof)  # [steps][hist, scan, pass0..]
+    local_pass_ms = float(lp[:, 2:].mean())
+    ph["local_global_histogram_ms"] = float(lp[:, 0].mean())
+    ph["local_digit_binning_pass_mean_ms"] = local_pass_ms
+    # kernels launched per sharded sort: MSD histogram + exchange pass (+ its scan in staged mode) + the local sort's
+    launches_per_sort = 1 + 1 + s.local_info("launches_per_sort")
     result = {
-        "ms_per_step": ms, "pass_ms": local_pass_ms, "kernel_ms": ph, "kernel": "digit_binning_wide_kernel (local sort) + fused NVLink exchange pass",
-        "variant": 2, "tile_keys": 16384, "rank_mode": "atomic", "e2e_ms_per_step": e2e_ms, "e2e_steps": e2e_steps,
-        "h2d_bytes": 4 * n, "d2h_bytes": 4 * int(out.numel()), "gpu_launches": args.steps * (2 + 1 + 6), "clocks": clocks,
+        "ms_per_step": ms, "pass_ms": local_pass_ms, "kernel_ms": ph, "phases_ms": ph,
+        "kernel": "digit_binning_wide_kernel (local sort) + fused NVLink exchange pass",
+        "variant": s.local_info("variant"), "tile_keys": s.local_info("tile_keys"),
+        "rank_mode": "atomic" if s.local_info("rank_mode") == 0 else "ballot", "e2e_ms_per_step": e2e_ms, "e2e_steps": e2e_steps,
+        "h2d_bytes": 4 * n, "d2h_bytes": 4 * int(out.numel()), "gpu_launches": args.steps * launches_per_sort, "clocks": clocks,
         "verified": bool(verified),
+        "e2e_api": "ShardedSorter.sort_host: torch pinned H2D copy + osb200_sharded_sort_keys_u32 (C-ABI) + torch D2H copy of the slice",
     }
     s.close()
     return result

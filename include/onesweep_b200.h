@@ -149,7 +149,9 @@ OSB200_API int osb200_get_profile(osb200_handle h, float* out_ms, int capacity);
  *                             it to all ranks (torch.distributed / MPI / files).
  *   osb200_sharded_create     every rank: joins the communicator (world ranks on ONE node), allocates
  *                             receive + local-sort workspace for up to max_n_local keys per rank plus
- *                             `slack_percent` head-room for bucket imbalance.
+ *                             `slack_percent` head-room for bucket imbalance.  max_n_local and slack_percent MUST
+ *                             be the same on every rank: if any rank's share exceeds that capacity, every rank
+ *                             returns OSB200_ERR_SIZE from the sort call together (no rank is left in a collective).
  *   osb200_sharded_sort_keys_u32
  *                             every rank passes its n_local unsorted keys.  After the call rank r owns
  *                             the r-th contiguous slice of the global ascending order: *d_out points

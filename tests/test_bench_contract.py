@@ -37,3 +37,19 @@ def test_own_arm_needs_a_gpu():
     r = subprocess.run([sys.executable, "bench.py", "--steps", "1", "--warmup", "1"], cwd=ROOT, capture_output=True,
                        text=True, timeout=300)
     assert r.returncode != 0 and r.stdout.strip() == ""  # no number is ever produced by a CPU path
+
+
+def test_both_arms_print_the_same_metric_and_workload_strings():
+    """The driver divides the two arms' values only if metric/unit/config agree: both lines are built from the same
+    constants (round 1 printed two different metric strings and got no ratio)."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"metric": METRIC') == 2 and src.count('"workload": workload(') == 2
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1"))
+    d = json.loads(r.stdout.strip())
+    import bench
+
+    assert d["metric"] == bench.METRIC and d["config"]["workload"] == bench.workload(bench.LOG2_N, 2)
+    # torchrun exports OMP_NUM_THREADS=1: the CPU leg must still use every physical core it may run on
+    assert d["cpu_baseline"]["cores"] == bench.HOST_THREADS >= 1

@@ -79,6 +79,46 @@ def test_pairs_u32_2pow30_stability(g):
     s.close()
 
 
+def test_pairs_u32_2pow30_bit_exact_vs_reference_cuda(g, reflib):
+    """BASELINE config 3 as SURVEY 8(d) states it: 2^30 (key, payload) pairs, keys AND payloads bit-exact against the
+    reference's own pairs kernels (OneSweep::DigitBinningPassPairs, Sort/OneSweep.cu:346-600) on identical input.
+    Payload = element index and 20-bit keys (~1024 duplicates of every key value): any instability in either
+    implementation would show as a payload mismatch."""
+    if reflib is None:
+        pytest.skip("oracle/_ref/libref_onesweep.so not built")
+    n = 1 << 30
+    k = torch.empty(n, dtype=torch.int32, device="cuda")
+    v = torch.empty(n, dtype=torch.int32, device="cuda")
+    g.init_random(k, 0, 10, payload=v, payload_is_index=True)
+    k &= 0xFFFFF
+    rk, rv = k.clone(), v.clone()
+    h = reflib.lib.ref_create(n)
+    assert h
+    ak, av = torch.empty_like(k), torch.empty_like(v)
+    assert reflib.lib.ref_sort_pairs(h, rk.data_ptr(), rv.data_ptr(), ak.data_ptr(), av.data_ptr(), n) == 0
+    torch.cuda.synchronize()
+    del ak, av
+    reflib.lib.ref_destroy(h)
+    torch.cuda.empty_cache()
+    s = g.OneSweepSorter(n, 4, 4)
+    s.sort_pairs(k, v)
+    torch.cuda.synchronize()
+    assert torch.equal(k, rk), "keys differ from the reference CUDA OneSweep"
+    assert torch.equal(v, rv), "payloads differ from the reference CUDA OneSweep"
+    # and with the reference's own payload = key input (UtilityKernels.cuh:85-117), full 32-bit keys
+    g.init_random(k, 0, 10, payload=v)
+    rk.copy_(k); rv.copy_(v)
+    s.sort_pairs(k, v)
+    s.close()
+    torch.cuda.empty_cache()
+    h = reflib.lib.ref_create(n)
+    ak, av = torch.empty_like(k), torch.empty_like(v)
+    assert reflib.lib.ref_sort_pairs(h, rk.data_ptr(), rv.data_ptr(), ak.data_ptr(), av.data_ptr(), n) == 0
+    torch.cuda.synchronize()
+    reflib.lib.ref_destroy(h)
+    assert torch.equal(k, rk) and torch.equal(v, rv)
+
+
 def test_keys_u64_2pow30(g):
     n = 1 << 30
     s = g.OneSweepSorter(n, 8, 0)

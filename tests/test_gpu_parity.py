@@ -40,6 +40,56 @@ def tile_keys(sorter):
     return sorter.info("tile_keys")
 
 
+# ---- against the reference's own CUDA kernels ------------------------------------------------------
+
+def test_bit_exact_vs_reference_cuda(g, sorter, reflib):
+    if reflib is None:
+        pytest.skip("oracle/_ref/libref_onesweep.so not built")
+    n = 1 << 22
+    h = reflib.lib.ref_create(n)
+    a, alt = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
+    pa, palt = torch.empty_like(a), torch.empty_like(a)
+    for size, seed in [(7680, 7680), (9999, 9999), (1 << 20, 10), (1 << 22, 22)]:
+        assert reflib.lib.ref_init_random_keys(a.data_ptr(), size, 0, seed) == 0
+        mine = a[:size].clone()
+        assert reflib.lib.ref_sort_keys(h, a.data_ptr(), alt.data_ptr(), size) == 0
+        sorter.sort_keys(mine)
+        torch.cuda.synchronize()
+        assert torch.equal(mine, a[:size]), f"keys n={size}"
+        # pairs, payload = key as the reference generates them
+        assert reflib.lib.ref_init_random_pairs(a.data_ptr(), pa.data_ptr(), size, 0, seed) == 0
+        mk, mv = a[:size].clone(), pa[:size].clone()
+        assert reflib.lib.ref_sort_pairs(h, a.data_ptr(), pa.data_ptr(), alt.data_ptr(), palt.data_ptr(), size) == 0
+        sorter.sort_pairs(mk, mv)
+        torch.cuda.synchronize()
+        assert torch.equal(mk, a[:size]) and torch.equal(mv, pa[:size]), f"pairs n={size}"
+        assert reflib.lib.ref_validate_keys(h, mk.data_ptr(), size) == 0  # the reference's own validator on OUR output
+    reflib.lib.ref_destroy(h)
+
+
+@pytest.mark.skipif(not os.path.exists(GOLDEN), reason="golden fixture not generated yet")
+def test_cuda_path_reproduces_reference_golden_vectors(g, oracle):
+    cases = json.load(open(GOLDEN))["cases"]
+    s = g.OneSweepSorter(max(c["n"] for c in cases), 4, 4)
+    for c in cases:
+        n = c["n"]
+        t = torch.empty(n, dtype=torch.int32, device="cuda")
+        p = torch.empty(n, dtype=torch.int32, device="cuda") if c["pairs"] else None
+        g.init_random(t, c["and_count"], c["seed"], payload=p)
+        assert oracle.digest(host_u32(t)) == c["input_digest"]
+        hist = s.global_histogram(t).cpu().numpy().astype(np.uint64)
+        assert oracle.digest(hist.reshape(-1)) == c["global_hist_digest"]
+        if c["pairs"]:
+            s.sort_pairs(t, p)
+            assert oracle.digest(host_u32(p)) == c["payload_digest"]
+        else:
+            s.sort_keys(t)
+        assert oracle.digest(host_u32(t)) == c["sorted_digest"]
+    s.close()
+
+
+# ---- against the oracle ------------------------------------------------------------------------------
+
 def test_atomic_rank_selftest_passed(sorter):
     assert sorter.info("atomic_order_ok") == 1
     assert sorter.info("rank_mode") == 0
@@ -278,51 +328,3 @@ def test_dispatcher_mirror_runs_reference_tests(g):
     assert passed == total
     with pytest.raises(ValueError):
         d.BatchTimingPairs(1 << 20, 1, 10)
-
-
-# ---- against the reference's own CUDA kernels ------------------------------------------------------
-
-def test_bit_exact_vs_reference_cuda(g, sorter, reflib):
-    if reflib is None:
-        pytest.skip("oracle/_ref/libref_onesweep.so not built")
-    n = 1 << 22
-    h = reflib.lib.ref_create(n)
-    a, alt = torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.int32, device="cuda")
-    pa, palt = torch.empty_like(a), torch.empty_like(a)
-    for size, seed in [(7680, 7680), (9999, 9999), (1 << 20, 10), (1 << 22, 22)]:
-        assert reflib.lib.ref_init_random_keys(a.data_ptr(), size, 0, seed) == 0
-        mine = a[:size].clone()
-        assert reflib.lib.ref_sort_keys(h, a.data_ptr(), alt.data_ptr(), size) == 0
-        sorter.sort_keys(mine)
-        torch.cuda.synchronize()
-        assert torch.equal(mine, a[:size]), f"keys n={size}"
-        # pairs, payload = key as the reference generates them
-        assert reflib.lib.ref_init_random_pairs(a.data_ptr(), pa.data_ptr(), size, 0, seed) == 0
-        mk, mv = a[:size].clone(), pa[:size].clone()
-        assert reflib.lib.ref_sort_pairs(h, a.data_ptr(), pa.data_ptr(), alt.data_ptr(), palt.data_ptr(), size) == 0
-        sorter.sort_pairs(mk, mv)
-        torch.cuda.synchronize()
-        assert torch.equal(mk, a[:size]) and torch.equal(mv, pa[:size]), f"pairs n={size}"
-        assert reflib.lib.ref_validate_keys(h, mk.data_ptr(), size) == 0  # the reference's own validator on OUR output
-    reflib.lib.ref_destroy(h)
-
-
-@pytest.mark.skipif(not os.path.exists(GOLDEN), reason="golden fixture not generated yet")
-def test_cuda_path_reproduces_reference_golden_vectors(g, oracle):
-    cases = json.load(open(GOLDEN))["cases"]
-    s = g.OneSweepSorter(max(c["n"] for c in cases), 4, 4)
-    for c in cases:
-        n = c["n"]
-        t = torch.empty(n, dtype=torch.int32, device="cuda")
-        p = torch.empty(n, dtype=torch.int32, device="cuda") if c["pairs"] else None
-        g.init_random(t, c["and_count"], c["seed"], payload=p)
-        assert oracle.digest(host_u32(t)) == c["input_digest"]
-        hist = s.global_histogram(t).cpu().numpy().astype(np.uint64)
-        assert oracle.digest(hist.reshape(-1)) == c["global_hist_digest"]
-        if c["pairs"]:
-            s.sort_pairs(t, p)
-            assert oracle.digest(host_u32(p)) == c["payload_digest"]
-        else:
-            s.sort_keys(t)
-        assert oracle.digest(host_u32(t)) == c["sorted_digest"]
-    s.close()
