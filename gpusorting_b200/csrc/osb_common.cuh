@@ -66,6 +66,7 @@ struct KeyCodec {
     uint32_t flags = 0;  // bit 0: encode keys right after loading; bit 1: decode keys right before storing
 };
 constexpr uint32_t kCodecEncodeOnLoad = 1u, kCodecDecodeOnStore = 2u;
+constexpr uint32_t kCodecFromPlan = 4u;  // encode/decode flags of a pass are taken from the device plan (first/last executed pass)
 
 template <typename KeyT> __device__ __forceinline__ KeyT codec_encode(KeyT k, KeyT a, KeyT b, KeyT d)
 {
@@ -84,6 +85,28 @@ template <typename KeyT> __device__ __forceinline__ KeyT codec_decode(KeyT e, Ke
 template <typename KeyT> __device__ __forceinline__ uint32_t digit_of(KeyT k, uint32_t shift)
 {
     return static_cast<uint32_t>(k >> shift) & (kRadix - 1);
+}
+// digit narrower than 8 bits (the last place of a begin_bit/end_bit sort): mask = 2^bits - 1
+template <typename KeyT> __device__ __forceinline__ uint32_t digit_of(KeyT k, uint32_t shift, uint32_t mask)
+{
+    return static_cast<uint32_t>(k >> shift) & mask;
+}
+
+// ---- device-side launch plan -----------------------------------------------------------------------------
+// Written by the scan kernel, read by every DigitBinningPass of the same sort: the host enqueues a fixed sequence of
+// launches and never synchronises, yet passes whose digit is the same for ALL keys (one non-empty bin in the global
+// histogram) move nothing.  Reference idea: the entropy benchmark of GPUSortingD3D12/Tests.h:383-393 shows what low-entropy
+// inputs cost; skipping is this repository's answer (the reference itself always runs its 4 passes).
+struct SortPlan {
+    uint32_t skip_mask;   // bit p: pass p is skipped (its CTAs exit at once)
+    uint32_t executed;    // number of passes that run; odd -> the result is in the alt buffers -> copy_back_kernel moves it
+    uint32_t first_exec;  // first / last executed pass (typed keys: encode in the first one, decode in the last one)
+    uint32_t last_exec;
+};
+// pass `place` reads the caller's buffers iff an even number of passes ran before it
+__device__ __forceinline__ bool plan_src_is_alt(const SortPlan& pl, uint32_t place)
+{
+    return __popc(~pl.skip_mask & ((1u << place) - 1u)) & 1u;
 }
 
 }  // namespace osb

@@ -4,8 +4,10 @@
 // it owns the ping-pong buffers and the control state and issues the launch plan of
 // OneSweepDispatcher.cuh:311-363 -- GlobalHistogram, Scan, then one DigitBinningPass per digit place,
 // ping-ponging keys -> alt -> keys.  Differences, all deliberate:
-//   * no per-sort memset of the tile descriptors (epoch-stamped 64-bit descriptors); one 8.3 KB memset of the
-//     control block (global histogram + tile tickets) per sort instead of 6 memsets over ~573 MB at n=2^30;
+//   * no per-sort memset of the 64-bit inclusive descriptors (epoch-stamped); per sort there are two memsets: the 8.3 KB
+//     control block (global histogram + tile tickets) and the compact 16-bit reductions (512 B per tile and place:
+//     128 MiB at n = 2^30 u32, ~20 us) -- against the reference's 6 memsets over ~573 MB at n = 2^30;
+//   * passes whose digit is the same for every key are skipped, decided on the device (osb::SortPlan);
 //   * no host synchronisation inside the sort; everything is enqueued on the caller's stream;
 //   * the caller owns keys/values.
 #include <cstdio>
@@ -37,7 +39,8 @@ struct ControlLayout {
     static constexpr size_t zeroed_bytes = ghist_bytes + ticket_bytes;
     static constexpr size_t gbase_bytes = kMaxPlaces * osb::kRadix * sizeof(unsigned long long);
     static constexpr size_t err_bytes = 64;
-    static constexpr size_t total = zeroed_bytes + gbase_bytes + err_bytes;
+    static constexpr size_t plan_bytes = 64;  // osb::SortPlan, written by the scan kernel of every sort
+    static constexpr size_t total = zeroed_bytes + gbase_bytes + err_bytes + plan_bytes;
 };
 
 }  // namespace
@@ -50,6 +53,7 @@ struct osb200_sorter {
     int value_bytes = 0;
     osb::BinningConfig cfg;
     bool atomic_order_ok = false;
+    bool short_circuit = true;   // skip passes whose digit is the same for all keys (decided on the device, no host sync)
 
     void* alt_keys = nullptr;
     uint32_t* alt_vals = nullptr;
@@ -75,6 +79,10 @@ struct osb200_sorter {
     unsigned long long* err() const
     {
         return reinterpret_cast<unsigned long long*>(control + ControlLayout::zeroed_bytes + ControlLayout::gbase_bytes);
+    }
+    osb::SortPlan* plan() const
+    {
+        return reinterpret_cast<osb::SortPlan*>(control + ControlLayout::zeroed_bytes + ControlLayout::gbase_bytes + ControlLayout::err_bytes);
     }
 };
 
@@ -108,21 +116,33 @@ int next_epoch(osb200_sorter* s, cudaStream_t stream, uint32_t* out)
 
 int check_handle(const osb200_sorter* s) { return s ? OSB200_OK : OSB200_ERR_INVALID_ARG; }
 
-// The launch plan (reference: OneSweepDispatcher.cuh:311-363).
+// The launch plan (reference: OneSweepDispatcher.cuh:311-363): GlobalHistogram, Scan, one DigitBinningPass per digit
+// place of [begin_bit, end_bit), then the (normally empty) copy-back.  Everything is enqueued on `stream`; which passes
+// actually move data is decided on the device (osb::SortPlan): the host never waits for the histogram.
 int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cudaStream_t stream,
-              const osb::KeyCodec* codec = nullptr)
+              const osb::KeyCodec* codec = nullptr, int begin_bit = 0, int end_bit = -1)
 {
-    if (n <= 1) return OSB200_OK;
+    const int key_bits = s->key_bytes * 8;
+    if (end_bit < 0) end_bit = key_bits;
+    if (begin_bit < 0 || end_bit > key_bits || begin_bit > end_bit) return OSB200_ERR_INVALID_ARG;
+    if (n <= 1 || begin_bit == end_bit) return OSB200_OK;
     if (n > s->max_n) return OSB200_ERR_SIZE;
     if (!d_keys || (reinterpret_cast<uintptr_t>(d_keys) & 15u)) return OSB200_ERR_INVALID_ARG;
     // d_vals == nullptr is a keys-only sort (also on a pairs-capable handle); the handle is never modified to say so
     if (d_vals && !s->value_bytes) return OSB200_ERR_INVALID_ARG;
-    const int places = s->key_bytes;
+    const int places = (end_bit - begin_bit + 7) / 8;
+    const uint32_t last_bits = static_cast<uint32_t>(end_bit - begin_bit - 8 * (places - 1));
+    const bool whole_key = begin_bit == 0 && end_bit == key_bits;
+    const bool wide = s->cfg.variant == osb::kVariantWide;
+    // the device plan (pass skipping, odd pass counts, bit ranges) is a feature of the default kernel
+    if (!wide && !whole_key) return OSB200_ERR_UNSUPPORTED;
+    const bool use_plan = wide;
 
     OSB_TRY(cudaMemsetAsync(s->control, 0, ControlLayout::zeroed_bytes, stream));
-    const bool wide = s->cfg.variant != osb::kVariantTilePerCta;  // every other variant uses the compact reductions
+    const bool compact = s->cfg.variant != osb::kVariantTilePerCta;  // every other variant uses the compact reductions
     const uint64_t agg_stride = tiles_for(n, osb::binning_tile_keys(s->key_bytes, d_vals != nullptr, s->cfg)) * osb::kRadix;
-    if (wide) OSB_TRY(cudaMemsetAsync(s->agg16, 0, agg_stride * places * sizeof(uint16_t), stream));
+    // reductions carry no epoch (16-bit words): they are cleared per sort, 512 B per tile and place (128 MiB at n = 2^30)
+    if (compact) OSB_TRY(cudaMemsetAsync(s->agg16, 0, agg_stride * places * sizeof(uint16_t), stream));
     int ne = 0;
     auto mark = [&]() -> cudaError_t {
         if (!s->profile) return cudaSuccess;
@@ -131,11 +151,15 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
     };
     s->ev_count = 0;
     OSB_TRY(mark());
-    osb::KeyCodec enc;  // typed keys: the histogram and the first pass see encoded keys, the last pass stores them decoded
+    osb::KeyCodec enc;  // typed keys: the histogram and the first executed pass see encoded keys, the last one stores them decoded
     if (codec) { enc = *codec; enc.flags = osb::kCodecEncodeOnLoad; }
-    OSB_TRY(osb::launch_global_histogram(d_keys, n, s->key_bytes, s->ghist(), s->sm_count, stream, codec ? &enc : nullptr));
+    if (whole_key)
+        OSB_TRY(osb::launch_global_histogram(d_keys, n, s->key_bytes, s->ghist(), s->sm_count, stream, codec ? &enc : nullptr));
+    else
+        OSB_TRY(osb::launch_global_histogram_bits(d_keys, n, s->key_bytes, s->ghist(), s->sm_count, stream, codec ? &enc : nullptr,
+                                                  static_cast<uint32_t>(begin_bit), places, last_bits));
     OSB_TRY(mark());
-    OSB_TRY(osb::launch_scan(s->ghist(), s->gbase(), places, stream));
+    OSB_TRY(osb::launch_scan(s->ghist(), s->gbase(), places, stream, use_plan ? s->plan() : nullptr, n, s->short_circuit));
     OSB_TRY(mark());
 
     void* src = d_keys;
@@ -147,19 +171,30 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
         int st = next_epoch(s, stream, &epoch);
         if (st != OSB200_OK) return st;
         osb::BinningConfig cfg = s->cfg;
+        cfg.digit_bits = p == places - 1 ? last_bits : 8u;
+        cfg.place = static_cast<uint32_t>(p);
+        if (use_plan) cfg.plan = s->plan();
         if (codec) {
             cfg.codec = *codec;
-            cfg.codec.flags = (p == 0 ? osb::kCodecEncodeOnLoad : 0u) | (p == places - 1 ? osb::kCodecDecodeOnStore : 0u);
+            cfg.codec.flags = use_plan ? osb::kCodecFromPlan
+                                       : (p == 0 ? osb::kCodecEncodeOnLoad : 0u) | (p == places - 1 ? osb::kCodecDecodeOnStore : 0u);
         }
-        OSB_TRY(osb::launch_digit_binning(src, dst, sv, dv, n, s->key_bytes, static_cast<uint32_t>(p) * 8u,
-                                          s->gbase() + p * osb::kRadix, s->desc, s->agg16 + p * agg_stride,
-                                          s->tickets() + p, epoch, cfg, stream));
+        // with a plan every launch gets (caller buffers, alt buffers) and picks its direction on the device
+        OSB_TRY(osb::launch_digit_binning(use_plan ? d_keys : src, use_plan ? s->alt_keys : dst, use_plan ? d_vals : sv,
+                                          use_plan ? (d_vals ? s->alt_vals : nullptr) : dv, n, s->key_bytes,
+                                          static_cast<uint32_t>(begin_bit + 8 * p), s->gbase() + p * osb::kRadix, s->desc,
+                                          s->agg16 + p * agg_stride, s->tickets() + p, epoch, cfg, stream));
         OSB_TRY(mark());
         void* t = src; src = dst; dst = t;
         uint32_t* tv = sv; sv = dv; dv = tv;
     }
+    // an odd number of EXECUTED passes leaves the result in the alt buffers.  Without skipping the count is known here
+    // (even for whole keys: no launch); with skipping only the device knows, and the kernel exits at once if it is even.
+    if (use_plan && (s->short_circuit || (places & 1)))
+        OSB_TRY(osb::launch_copy_back(s->plan(), s->alt_keys, d_keys, d_vals ? s->alt_vals : nullptr, d_vals, n, s->key_bytes,
+                                      s->sm_count, stream));
     s->ev_count = ne;
-    return OSB200_OK;  // even number of passes: result is back in d_keys / d_vals
+    return OSB200_OK;
 }
 
 int ensure_staging(osb200_sorter* s)
@@ -222,8 +257,11 @@ int osb_internal_binning_pass(osb200_handle h, const void* d_in, void* d_out, ui
     uint32_t epoch = 0;
     int st = next_epoch(h, stream, &epoch);
     if (st != OSB200_OK) return st;
+    osb::BinningConfig cfg = h->cfg;
+    const uint32_t key_bits = static_cast<uint32_t>(h->key_bytes) * 8u;
+    cfg.digit_bits = key_bits - shift < 8u ? key_bits - shift : 8u;  // a shift within 8 bits of the top: fewer than 256 bins
     OSB_TRY(osb::launch_digit_binning(d_in, d_out, nullptr, nullptr, n, h->key_bytes, shift, base, h->desc, h->agg16,
-                                      h->tickets(), epoch, h->cfg, stream));
+                                      h->tickets(), epoch, cfg, stream));
     return OSB200_OK;
 }
 
@@ -368,6 +406,13 @@ int osb200_sort_keys_typed(osb200_handle h, void* d_keys, uint64_t n, int key_ty
     return sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream), plain ? nullptr : &c);
 }
 
+int osb200_sort_bits(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int begin_bit, int end_bit, void* stream)
+{
+    if (check_handle(h) != OSB200_OK) return OSB200_ERR_INVALID_ARG;
+    if (d_values && (h->key_bytes != 4 || h->value_bytes != 4)) return OSB200_ERR_INVALID_ARG;
+    return sort_impl(h, d_keys, d_values, n, static_cast<cudaStream_t>(stream), nullptr, begin_bit, end_bit);
+}
+
 int osb200_sort_pairs_typed(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int key_type, int descending,
                             void* stream)
 {
@@ -434,8 +479,11 @@ int osb200_digit_binning_pass(osb200_handle h, const void* d_in, void* d_out, co
     uint32_t epoch = 0;
     st = next_epoch(h, q, &epoch);
     if (st != OSB200_OK) return st;
+    osb::BinningConfig cfg = h->cfg;
+    const uint32_t key_bits = static_cast<uint32_t>(h->key_bytes) * 8u;
+    cfg.digit_bits = key_bits - radix_shift < 8u ? key_bits - radix_shift : 8u;
     OSB_TRY(osb::launch_digit_binning(d_in, d_out, d_in_values, d_out_values, n, h->key_bytes, radix_shift, h->gbase(), h->desc,
-                                      h->agg16, h->tickets(), epoch, h->cfg, q));
+                                      h->agg16, h->tickets(), epoch, cfg, q));
     return OSB200_OK;
 }
 
@@ -475,6 +523,17 @@ int osb200_set_option(osb200_handle h, const char* key, int64_t value)
         return OSB200_OK;
     }
     if (!std::strcmp(key, "profile")) { h->profile = value != 0; return OSB200_OK; }
+    if (!std::strcmp(key, "short_circuit")) { h->short_circuit = value != 0; return OSB200_OK; }
+    if (!std::strcmp(key, "spin_cap")) {
+        if (value < 1 || value > (1ll << 30)) return OSB200_ERR_INVALID_ARG;
+        h->cfg.spin_cap = static_cast<uint32_t>(value);
+        return OSB200_OK;
+    }
+    if (!std::strcmp(key, "debug_stall_every")) {  // test hook of the forward-progress fallback (0 = off)
+        if (value < 0 || value > (1ll << 30)) return OSB200_ERR_INVALID_ARG;
+        h->cfg.debug_stall_every = static_cast<uint32_t>(value);
+        return OSB200_OK;
+    }
     if (!std::strcmp(key, "variant")) {
         if (value < 0 || value >= osb::kNumVariants) return OSB200_ERR_INVALID_ARG;
         h->cfg.variant = static_cast<int>(value);
@@ -497,8 +556,19 @@ int64_t osb200_get_info(osb200_handle h, const char* key)
 {
     if (check_handle(h) != OSB200_OK || !key) return OSB200_ERR_INVALID_ARG;
     if (!std::strcmp(key, "tile_keys")) return osb::binning_tile_keys(h->key_bytes, h->value_bytes != 0, h->cfg);
-    if (!std::strcmp(key, "launches_per_sort")) return 2 + h->key_bytes;  // histogram + scan + one pass per place
+    if (!std::strcmp(key, "launches_per_sort")) {  // histogram + scan + one pass per place (+ copy-back: keys [+ values])
+        const bool cb = h->cfg.variant == osb::kVariantWide && h->short_circuit;
+        return 2 + h->key_bytes + (cb ? (h->value_bytes ? 2 : 1) : 0);
+    }
     if (!std::strcmp(key, "memsets_per_sort")) return h->cfg.variant != osb::kVariantTilePerCta ? 2 : 1;
+    if (!std::strcmp(key, "short_circuit")) return h->short_circuit ? 1 : 0;
+    if (!std::strcmp(key, "spin_cap")) return h->cfg.spin_cap;
+    if (!std::strcmp(key, "last_skip_mask") || !std::strcmp(key, "last_executed_passes")) {
+        // the plan of the last sort on this handle (synchronises the device: introspection / tests only)
+        osb::SortPlan pl;
+        if (cudaMemcpy(&pl, h->plan(), sizeof(pl), cudaMemcpyDeviceToHost) != cudaSuccess) return OSB200_ERR_CUDA;
+        return key[5] == 's' ? static_cast<int64_t>(pl.skip_mask) : static_cast<int64_t>(pl.executed);
+    }
     if (!std::strcmp(key, "sm_count")) return h->sm_count;
     if (!std::strcmp(key, "rank_mode")) return h->cfg.rank_mode;
     if (!std::strcmp(key, "variant")) return h->cfg.variant;

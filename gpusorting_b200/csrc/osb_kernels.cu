@@ -188,30 +188,134 @@ cudaError_t launch_digit_histogram(const void* keys, uint64_t n, int key_bytes, 
 }
 
 // =====================================================================================================
-// Scan: exclusive prefix over the 256 bins of each digit place
+// Scan: exclusive prefix over the 256 bins of each digit place (reference: OneSweep::Scan, OneSweep.cu:125-162), and --
+// new here -- the device-side launch plan: a place whose histogram has ONE non-empty bin (all n keys share that digit)
+// is marked skipped, so its DigitBinningPass exits at once; the passes derive their source/destination from the
+// number of executed passes before them, and a final copy moves the result home if that number is odd.
+// One CTA walks the (at most 8) places: the plan needs all of them.
 // =====================================================================================================
 __global__ void __launch_bounds__(kRadix)
-scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ gbase)
+scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ gbase, int places,
+            SortPlan* plan, unsigned long long n, int allow_skip)
 {
     __shared__ unsigned long long s_warp[kRadix / 32];
     const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
-    const unsigned long long c = ghist[blockIdx.x * kRadix + d];
-    unsigned long long incl = c;
+    uint32_t skip_mask = 0;
+    for (int p = 0; p < places; ++p) {
+        const unsigned long long c = ghist[p * kRadix + d];
+        unsigned long long incl = c;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        const int single_bin = __syncthreads_or(plan != nullptr && allow_skip && c == n);
+        unsigned long long pre = 0;
+        for (int w = 0; w < warp; ++w) pre += s_warp[w];
+        gbase[p * kRadix + d] = pre + incl - c;
+        if (single_bin) skip_mask |= 1u << p;
+        __syncthreads();  // s_warp is reused by the next place
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    unsigned long long pre = 0;
-    for (int w = 0; w < warp; ++w) pre += s_warp[w];
-    gbase[blockIdx.x * kRadix + d] = pre + incl - c;
+    if (plan != nullptr && d == 0) {
+        SortPlan pl;
+        pl.skip_mask = skip_mask;
+        const uint32_t run = ~skip_mask & ((places >= 32 ? 0u : (1u << places)) - 1u);
+        pl.executed = __popc(run);
+        pl.first_exec = run ? static_cast<uint32_t>(__ffs(run) - 1) : 0xffffffffu;
+        pl.last_exec = run ? static_cast<uint32_t>(31 - __clz(run)) : 0xffffffffu;
+        *plan = pl;
+    }
 }
 
-cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream)
+cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream,
+                        SortPlan* plan, uint64_t n, bool allow_skip)
 {
-    scan_kernel<<<places, kRadix, 0, stream>>>(ghist, gbase);
+    scan_kernel<<<1, kRadix, 0, stream>>>(ghist, gbase, places, plan, n, allow_skip ? 1 : 0);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// GlobalHistogram for begin_bit/end_bit sorts: digit places start at an arbitrary bit and the last one may be narrower
+// than 8 bits, so the digits are extracted key by key (the byte-aligned kernel above slices the loaded words directly).
+// Same bank-private column layout.
+// =====================================================================================================
+template <typename KeyT>
+__global__ void __launch_bounds__(kHistThreads, 1)
+global_histogram_bits_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ ghist, KeyCodec codec,
+                             uint32_t begin_bit, int places, uint32_t last_mask)
+{
+    constexpr int COLS = HistGeom<KeyT>::COLS;
+    extern __shared__ __align__(16) uint32_t s_hist[];  // [places * 256][COLS]
+    const int bins = places * kRadix;
+    for (int i = threadIdx.x; i < bins * COLS; i += kHistThreads) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t* s_col = s_hist + (threadIdx.x & (COLS - 1));
+    const bool enc = codec.flags & kCodecEncodeOnLoad;
+    const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kHistThreads;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kHistThreads + threadIdx.x; i < n; i += stride) {
+        KeyT k = __ldcs(keys + i);
+        if (enc) k = codec_encode<KeyT>(k, ca, cb, cd);
+        for (int p = 0; p < places; ++p) {
+            const uint32_t dg = digit_of(k, begin_bit + 8u * p, p == places - 1 ? last_mask : 255u);
+            atomicAdd(&s_col[(p * kRadix + dg) * COLS], 1u);
+        }
+    }
+    __syncthreads();
+    for (int bin = threadIdx.x; bin < bins; bin += kHistThreads) {
+        uint32_t sum = 0;
+#pragma unroll 8
+        for (int c = 0; c < COLS; ++c) sum += s_hist[bin * COLS + ((c + threadIdx.x) & (COLS - 1))];
+        if (sum) atomicAdd(&ghist[bin], static_cast<unsigned long long>(sum));
+    }
+}
+
+cudaError_t launch_global_histogram_bits(const void* keys, uint64_t n, int key_bytes, unsigned long long* ghist, int sm_count,
+                                         cudaStream_t stream, const KeyCodec* codec_in, uint32_t begin_bit, int places,
+                                         uint32_t last_bits)
+{
+    const KeyCodec codec = codec_in ? *codec_in : KeyCodec();
+    uint64_t want = (n + kHistThreads * 4 - 1) / (kHistThreads * 4);
+    if (want < 1) want = 1;
+    const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) ? want : sm_count);
+    const uint32_t last_mask = (1u << last_bits) - 1u;
+    if (key_bytes == 4)
+        global_histogram_bits_kernel<uint32_t><<<grid, kHistThreads, hist_smem_bytes<uint32_t>(), stream>>>(
+            static_cast<const uint32_t*>(keys), n, ghist, codec, begin_bit, places, last_mask);
+    else
+        global_histogram_bits_kernel<uint64_t><<<grid, kHistThreads, hist_smem_bytes<uint64_t>(), stream>>>(
+            static_cast<const uint64_t*>(keys), n, ghist, codec, begin_bit, places, last_mask);
+    return cudaGetLastError();
+}
+
+// =====================================================================================================
+// copy_back: an odd number of executed passes leaves the result in the alt buffers
+// =====================================================================================================
+__global__ void __launch_bounds__(512)
+copy_back_kernel(const SortPlan* __restrict__ plan, const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t vecs,
+                 const unsigned char* __restrict__ src_tail, unsigned char* __restrict__ dst_tail, uint32_t tail_bytes)
+{
+    if (!(plan->executed & 1u)) return;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < vecs; i += stride) __stcs(dst + i, __ldcs(src + i));
+    if (blockIdx.x == 0 && threadIdx.x < tail_bytes) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+
+cudaError_t launch_copy_back(const SortPlan* plan, const void* alt_keys, void* keys, const uint32_t* alt_vals, uint32_t* vals,
+                             uint64_t n, int key_bytes, int sm_count, cudaStream_t stream)
+{
+    auto one = [&](const void* s, void* d, uint64_t bytes) {
+        const uint64_t vecs = bytes / 16;
+        uint64_t want = (vecs + 511) / 512;
+        if (want < 1) want = 1;
+        const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) * 4 ? want : sm_count * 4);
+        copy_back_kernel<<<grid, 512, 0, stream>>>(plan, static_cast<const uint4*>(s), static_cast<uint4*>(d), vecs,
+                                                   static_cast<const unsigned char*>(s) + vecs * 16,
+                                                   static_cast<unsigned char*>(d) + vecs * 16, static_cast<uint32_t>(bytes - vecs * 16));
+    };
+    one(alt_keys, keys, n * key_bytes);
+    if (vals) one(alt_vals, vals, n * sizeof(uint32_t));
     return cudaGetLastError();
 }
 
@@ -489,17 +593,50 @@ __device__ __forceinline__ void st_relaxed_gpu_u16(uint16_t* p, uint32_t v)
     asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(p), "h"(static_cast<uint16_t>(v)) : "memory");
 }
 
+// What a digit thread needs to re-reduce a predecessor tile by itself (forward-progress fallback).
+template <typename KeyT>
+struct TileRereduce {
+    const KeyT* in;      // this pass's input keys
+    uint32_t tile_keys;  // T
+    uint32_t shift, mask;
+    bool encode;         // typed keys, first executed pass: the digits are those of the ENCODED keys
+    KeyT ca, cb, cd;
+};
+
+// Forward-progress fallback (reference: EmulatedDeadlocking.cu:159-267, SweepCommon.hlsl:317-425 -- a thread block that
+// has spun too long on a predecessor's flag stops waiting and computes that tile's reduction itself).  Here every digit
+// thread that gives up on tile x counts ITS digit over the tile's keys (the whole warp reads the same key: one
+// broadcast transaction per load; predecessor tiles are never the ragged last tile) and publishes the reduction on the
+// owner's behalf -- the value is the one the owner would write, so concurrent publishers agree.
+template <typename KeyT>
+__device__ __noinline__ uint32_t rereduce_tile(const TileRereduce<KeyT>& rr, uint16_t* agg16, int64_t x, uint32_t d)
+{
+    const KeyT* p = rr.in + static_cast<uint64_t>(x) * rr.tile_keys;
+    uint32_t c = 0;
+#pragma unroll 8
+    for (uint32_t i = 0; i < rr.tile_keys; ++i) {
+        KeyT k = p[i];
+        if (rr.encode) k = codec_encode<KeyT>(k, rr.ca, rr.cb, rr.cd);
+        c += digit_of(k, rr.shift, rr.mask) == d;
+    }
+    st_relaxed_gpu_u16(agg16 + x * kRadix + d, kAggReady | c);
+    return c;
+}
+
 // Decoupled lookback over the compact reductions.  Examines up to LOOK predecessors per round trip, with an
 // inclusive-prefix probe every STEP tiles.  Returns the number of keys with digit d in all predecessor tiles
 // (relative to the start of the array: the global digit base is added by the caller, so descriptor values stay
-// below n even when the bases are peer addresses in the sharded exchange pass).
-template <int LOOK, int STEP>
+// below n even when the bases are peer addresses in the sharded exchange pass).  A predecessor whose reduction is
+// still missing after spin_cap polls is re-reduced by this thread (rereduce_tile): the spin is bounded.
+template <int LOOK, int STEP, typename KeyT>
 __device__ __forceinline__ unsigned long long
-lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d, uint32_t epoch)
+lookback_wide(uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d, uint32_t epoch, uint32_t spin_cap,
+              const TileRereduce<KeyT>& rr)
 {
     static_assert(LOOK % STEP == 0, "probe spacing must divide the window");
     unsigned long long sum = 0;                       // reductions of tiles (cur, tile-1] already added
     int64_t cur = static_cast<int64_t>(tile) - 1;     // nearest predecessor not yet accounted for
+    uint32_t polls = 0;                               // consecutive unsuccessful polls of tile `cur`
     while (true) {
         if (cur < 0) return sum;
         uint32_t a[LOOK];
@@ -529,19 +666,50 @@ lookback_wide(const uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint
             run += a[i] & 0x7fffu;
         }
         sum = run;
+        if (stalled) {
+            polls = next == cur ? polls + 1 : 1;
+            if (polls > spin_cap) {
+                // maybe the stalled tile has finished altogether meanwhile: its inclusive prefix settles everything
+                const uint64_t v = ld_relaxed_gpu_u64(incl64 + next * kRadix + d);
+                if (desc_epoch(v) == epoch && (v & kFlagMask) == kFlagInclusive) return sum + desc_value(v);
+                sum += rereduce_tile<KeyT>(rr, agg16, next, d);
+                --next;
+                polls = 0;
+            } else {
+                __nanosleep(40);
+            }
+        } else {
+            polls = 0;
+        }
         cur = next;
-        if (stalled) __nanosleep(40);
     }
 }
 
-// OSB_EXP: compile-time experiments for tools/sweep.sh, OFF (0) in the product build.  Not yet measured on hardware:
+// OSB_EXP: compile-time experiments for tools/sweep.sh, OFF (0) in the product build (measured in round 2,
+// profiles/r02_experiments.md):
 //   bit 0 (1): 32-bit element offsets per digit instead of 64-bit byte pointers in the scatter (valid for n <= 2^32, out != 0)
-//   bit 1 (2): 256-bin passes store run by run, warp-owned digits, in chunks aligned to the destination's 128-byte lines
 //   bit 2 (4): the chained-scan lookback runs BEFORE the rank phase (digit warps look back while the other warps rank)
 //   bit 3 (8): full tiles are staged by ONE TMA bulk copy (cp.async.bulk + mbarrier) into the sorted-tile buffer, then LDS
 #ifndef OSB_EXP
 #define OSB_EXP 0
 #endif
+// OSB_ABL: timing-only ablations for tools/sweep.sh (the output is WRONG; never set in the product build):
+//   1 no lookback (prior = tile * const)   2 no global stores in the scatter   4 no count atomics   8 no rank atomics / transposing stores
+//   16 no scatter loop at all (use with 2)
+#ifndef OSB_ABL
+#define OSB_ABL 0
+#endif
+
+// Per-launch parameters of one DigitBinningPass.
+struct PassParams {
+    uint32_t shift;        // bit position of this pass's digit
+    uint32_t dbits;        // digit width, 1..8
+    uint32_t epoch;        // descriptor epoch of this launch
+    uint32_t place;        // index of this pass in the plan
+    uint32_t spin_cap;     // lookback polls before the fallback re-reduction
+    uint32_t stall_every;  // test hook (0 = off): tiles with tile % N == N-1 never publish their reduction
+    const SortPlan* plan;  // device plan or null
+};
 
 template <typename KeyT, bool PAIRS, int K, int WARPS>
 struct WideSmem {
@@ -552,25 +720,21 @@ struct WideSmem {
     alignas(16) uint32_t hist[WARPS * kRadix];       // warp-private digit counters (counts, then running slots)
     unsigned long long keyptr[kRadix];               // per digit: byte address of out[first key of the digit - tile slot]
     unsigned long long valptr[PAIRS ? kRadix : 1];
-    uint32_t run[(OSB_EXP & 2) ? kRadix : 32];       // run-by-run scatter: first slot (low 16 bits) | live length (high 16)
+    uint32_t run[32];                                // few-bins passes: first slot (low 16 bits) | live length (high 16)
 #if OSB_EXP & 1
     uint32_t off32[kRadix];                          // element index of tile slot 0 "as if" of this digit, mod 2^32
 #endif
-#if OSB_EXP & 2
-    uint32_t longmask[kRadix / 32];                  // digits whose run is long enough to be stored by the whole CTA
-#endif
     uint32_t wtot[kRadix / 32];
-    uint32_t tile;
+    uint32_t tile;                                   // this CTA's tile, 0xffffffff = the plan skips this pass
+    uint32_t plan_bits;                              // bit 0: source is the alt buffer; bits 1-2: codec flags of this pass
     alignas(8) uint64_t bar;                         // (TMA tile load) "tile landed" mbarrier
 };
 
-
 template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
-digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, const uint32_t* __restrict__ in_val,
-                          uint32_t* __restrict__ out_val, uint64_t n, uint32_t shift,
+digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1, uint64_t n,
                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
-                          uint32_t* ticket, uint32_t epoch, KeyCodec codec)
+                          uint32_t* ticket, PassParams pp, KeyCodec codec)
 {
     using S = WideSmem<KeyT, PAIRS, K, WARPS>;
     constexpr int THREADS = S::THREADS;
@@ -582,25 +746,49 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
     uint32_t* wh = sm.hist + warp * kRadix;
+    const uint32_t shift = pp.shift, epoch = pp.epoch;
+    const uint32_t dmask = (1u << pp.dbits) - 1u;
 
     {
         uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
         for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        const uint32_t t = atomicAdd(ticket, 1u);  // dynamic tile id: predecessors are already scheduled
+        // The device plan (if any) decides whether this pass runs at all, which buffer it reads, and -- typed keys --
+        // whether it is the pass that encodes / decodes.  Without a plan the launch arguments are taken as they are.
+        uint32_t bits = (codec.flags & (kCodecEncodeOnLoad | kCodecDecodeOnStore)) << 1;
+        bool skip = false;
+        if (pp.plan != nullptr) {
+            const SortPlan pl = *pp.plan;
+            skip = (pl.skip_mask >> pp.place) & 1u;
+            bits = plan_src_is_alt(pl, pp.place) ? 1u : 0u;
+            if (codec.flags & kCodecFromPlan)
+                bits |= (pp.place == pl.first_exec ? kCodecEncodeOnLoad << 1 : 0u) | (pp.place == pl.last_exec ? kCodecDecodeOnStore << 1 : 0u);
+        }
+        sm.plan_bits = bits;
+        const uint32_t t = skip ? 0xffffffffu : atomicAdd(ticket, 1u);  // dynamic tile id: predecessors are already scheduled
         sm.tile = t;
 #if OSB_EXP & 8
         mbar_init(&sm.bar, 1);
         fence_mbar_init();
-        if (static_cast<uint64_t>(t) * T + T <= n) {
+        if (!skip && static_cast<uint64_t>(t) * T + T <= n) {
+            const KeyT* src = (bits & 1u) ? buf1 : buf0;
             mbar_expect_tx(&sm.bar, T * sizeof(KeyT));
-            tma_load_1d(sm.sorted, in + static_cast<uint64_t>(t) * T, T * sizeof(KeyT), &sm.bar);
+            tma_load_1d(sm.sorted, src + static_cast<uint64_t>(t) * T, T * sizeof(KeyT), &sm.bar);
         }
 #endif
     }
     __syncthreads();
     const uint32_t tile = sm.tile;
+    if (tile == 0xffffffffu) return;  // all keys share this digit: nothing to move (the plan accounts for the parity)
+    const uint32_t plan_bits = sm.plan_bits;
+    const bool swap = plan_bits & 1u;
+    const uint32_t cflags = plan_bits >> 1;
+    const KeyT* __restrict__ in = swap ? buf1 : buf0;
+    KeyT* __restrict__ out = swap ? buf0 : buf1;
+    const uint32_t* __restrict__ in_val = swap ? val1 : val0;
+    uint32_t* __restrict__ out_val = swap ? val0 : val1;
+
     const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
     const bool full = tile_base + T <= n;
     const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
@@ -631,11 +819,11 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
         }
     }
 
-    // typed keys: the first pass of a sort turns the caller's keys into order-equivalent unsigned keys.  The padding of
-    // the ragged last tile is encoded too and stays the largest key only if it was loaded as the pre-image of all-ones,
-    // so it is simply re-set after encoding.
-    if (codec.flags & kCodecEncodeOnLoad) {
-        const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
+    // typed keys: the first executed pass of a sort turns the caller's keys into order-equivalent unsigned keys.  The
+    // padding of the ragged last tile is encoded too and stays the largest key only if it was loaded as the pre-image of
+    // all-ones, so it is simply re-set after encoding.
+    const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
+    if (cflags & kCodecEncodeOnLoad) {
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             key[i] = codec_encode<KeyT>(key[i], ca, cb, cd);
@@ -644,8 +832,10 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     }
 
     // ---- phase 1: count digits per warp (order-free, non-returning atomics) ---------------------------
+#if !(OSB_ABL & 4)
 #pragma unroll
-    for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift)], 1u);
+    for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift, dmask)], 1u);
+#endif
     __syncthreads();
 
     // ---- per digit: tile reduction -> publish; scan over digits; per-warp slot bases --------------------
@@ -653,7 +843,9 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     if (tid < kRadix) {
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
-        st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+        // (test hook: a "stalled" tile never publishes its reduction; its successors must re-reduce it themselves)
+        if (pp.stall_every == 0 || (tile % pp.stall_every) != pp.stall_every - 1)
+            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
     }
     tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
     if (tid < kRadix) {
@@ -663,74 +855,65 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
     }
     __syncthreads();
 
-#if OSB_EXP & 4
-    // ---- chained scan with decoupled lookback ------------------------------------------------------------
-    if (tid < kRadix) {
-        const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch);
-        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
-                           desc_pack(epoch, kFlagInclusive, prior + tile_count));
-        const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
-        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
-        if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
-        if (tid < 32 || (OSB_EXP & 2)) {
-            // the all-ones padding of the ragged last tile sits at the end of the run of its digit: not live
-            const uint32_t pad_digit = digit_of(static_cast<KeyT>(~static_cast<KeyT>(0)), shift);
-            const uint32_t live = tile_count - ((tid == pad_digit && !full) ? (T - valid) : 0u);
-            sm.run[tid] = tile_excl | (live << 16);
-#if OSB_EXP & 2
-            const uint32_t lm = __ballot_sync(0xffffffffu, live > 1024u);
-            if (lane == 0) sm.longmask[warp] = lm;
+    // ---- chained scan with decoupled lookback (one thread per digit) -------------------------------------
+    auto chained_scan = [&]() {
+        if (tid < kRadix) {
+#if OSB_ABL & 1
+            const unsigned long long prior = static_cast<unsigned long long>(tile) * (T / kRadix - 4);  // ~uniform input: realistic addresses, in bounds
+#else
+            TileRereduce<KeyT> rr;
+            rr.in = in; rr.tile_keys = T; rr.shift = shift; rr.mask = dmask;
+            rr.encode = cflags & kCodecEncodeOnLoad; rr.ca = ca; rr.cb = cb; rr.cd = cd;
+            const unsigned long long prior = lookback_wide<LOOK, STEP, KeyT>(agg16, incl64, tile, tid, epoch, pp.spin_cap, rr);
+#endif
+            st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
+                               desc_pack(epoch, kFlagInclusive, prior + tile_count));
+            const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
+            sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
+            if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
+            if (tid < 32) {
+                // the all-ones padding of the ragged last tile sits at the end of the run of its digit: not live
+                const uint32_t pad_digit = digit_of(static_cast<KeyT>(~static_cast<KeyT>(0)), shift, dmask);
+                const uint32_t live = tile_count - ((tid == pad_digit && !full) ? (T - valid) : 0u);
+                sm.run[tid] = tile_excl | (live << 16);
+            }
+#if OSB_EXP & 1
+            sm.off32[tid] = static_cast<uint32_t>(first);
 #endif
         }
-#if OSB_EXP & 1
-        sm.off32[tid] = static_cast<uint32_t>(first);
+    };
+#if OSB_EXP & 4
+    chained_scan();
 #endif
-    }
-#endif
+
     // ---- phase 2: the returning atomic hands every key its slot in the digit-sorted tile -----------------
     // (typed keys: the last pass stores the keys decoded; the digit was taken from the encoded key, and the scatter
     // below re-derives it from the tile, so the decoded form is produced only at the very end, in the store)
+#if OSB_ABL & 8
+#pragma unroll
+    for (int i = 0; i < K; ++i) asm volatile("" ::"l"(static_cast<unsigned long long>(key[i])) : "memory");  // keep the loads live
+#else
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt);
+        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift, dmask), lt);
         sm.sorted[slot] = key[i];
         if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
     }
+#endif
 
 #if !(OSB_EXP & 4)
-    // ---- chained scan with decoupled lookback ------------------------------------------------------------
-    if (tid < kRadix) {
-        const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch);
-        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
-                           desc_pack(epoch, kFlagInclusive, prior + tile_count));
-        const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
-        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + first * sizeof(KeyT);
-        if constexpr (PAIRS) sm.valptr[tid] = reinterpret_cast<unsigned long long>(out_val) + first * sizeof(uint32_t);
-        if (tid < 32 || (OSB_EXP & 2)) {
-            // the all-ones padding of the ragged last tile sits at the end of the run of its digit: not live
-            const uint32_t pad_digit = digit_of(static_cast<KeyT>(~static_cast<KeyT>(0)), shift);
-            const uint32_t live = tile_count - ((tid == pad_digit && !full) ? (T - valid) : 0u);
-            sm.run[tid] = tile_excl | (live << 16);
-#if OSB_EXP & 2
-            const uint32_t lm = __ballot_sync(0xffffffffu, live > 1024u);
-            if (lane == 0) sm.longmask[warp] = lm;
-#endif
-        }
-#if OSB_EXP & 1
-        sm.off32[tid] = static_cast<uint32_t>(first);
-#endif
-    }
+    chained_scan();
 #endif
     __syncthreads();
 
     // ---- scatter -----------------------------------------------------------------------------------------
-    // Few bins (a pass on the top <= 5 bits: the sharded exchange on log2(R) bits): runs are thousands of keys long, so
+    // Few bins (a digit of <= 5 bits: the sharded exchange on log2(R) bits): runs are thousands of keys long, so
     // the stores are issued run by run in chunks that start on 128-byte boundaries of the DESTINATION -- every warp
     // store is then one full line (4 full sectors), which is what keeps NVLink peer stores at their aligned rate
     // (profiles/r01_p2p_store_ub.txt: 128-B aligned 680-716 GB/s vs 390-580 GB/s at 4-byte alignment).
-    constexpr uint32_t kKeyBits = sizeof(KeyT) * 8;
-    if (kKeyBits - shift <= 5) {
-        const uint32_t nbins = 1u << (kKeyBits - shift);
+    const bool dec = cflags & kCodecDecodeOnStore;
+    if (pp.dbits <= 5) {
+        const uint32_t nbins = 1u << pp.dbits;
         for (uint32_t b = 0; b < nbins; ++b) {
             const uint32_t rd = sm.run[b];
             const uint32_t lo = rd & 0xffffu, len = rd >> 16;
@@ -743,71 +926,47 @@ digit_binning_wide_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
                 if (p >= ga) {
                     const uint32_t x = lo + p - ga;
                     KeyT k = sm.sorted[x];
-                    if (codec.flags & kCodecDecodeOnStore) k = codec_decode<KeyT>(k, static_cast<KeyT>(codec.a), static_cast<KeyT>(codec.b), static_cast<KeyT>(codec.d));
+                    if (dec) k = codec_decode<KeyT>(k, ca, cb, cd);
                     st_stream(reinterpret_cast<KeyT*>(kp) + x, k);
                     if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[b]) + x, sm.sorted_val[x]);
                 }
             }
         }
-#if OSB_EXP & 2
-    } else if (full && !(codec.flags & kCodecDecodeOnStore) && !PAIRS) {
-        // (experiment) every warp stores the runs of "its" digits, chunk-aligned to the destination lines ...
-        constexpr uint32_t kLine = 128 / sizeof(KeyT);
-        for (uint32_t d = warp; d < kRadix; d += WARPS) {
-            const uint32_t rd = sm.run[d];
-            const uint32_t lo = rd & 0xffffu, len = rd >> 16;
-            if (len == 0 || len > 1024u) continue;
-            const unsigned long long kp = sm.keyptr[d];
-            const uint32_t ga = static_cast<uint32_t>((kp / sizeof(KeyT) + lo) & (kLine - 1));
-            const uint32_t total = len + ga;
-            for (uint32_t p = lane; p < total; p += 32) {
-                if (p >= ga) { const uint32_t x = lo + p - ga; st_stream(reinterpret_cast<KeyT*>(kp) + x, sm.sorted[x]); }
-            }
-        }
-        // ... and runs longer than 1024 keys (skewed inputs) are stored by the whole CTA, as in the few-bins path
-        for (uint32_t wd = 0; wd < kRadix / 32; ++wd) {
-            uint32_t m = sm.longmask[wd];
-            while (m) {
-                const uint32_t d = wd * 32 + (__ffs(m) - 1);
-                m &= m - 1;
-                const uint32_t rd = sm.run[d];
-                const uint32_t lo = rd & 0xffffu, len = rd >> 16;
-                const unsigned long long kp = sm.keyptr[d];
-                const uint32_t ga = static_cast<uint32_t>((kp / sizeof(KeyT) + lo) & (kLine - 1));
-                const uint32_t total = len + ga;
-                for (uint32_t p = tid; p < total; p += THREADS) {
-                    if (p >= ga) { const uint32_t x = lo + p - ga; st_stream(reinterpret_cast<KeyT*>(kp) + x, sm.sorted[x]); }
-                }
-            }
-        }
-#endif
 #if OSB_EXP & 1
-    } else if (full && !(codec.flags & kCodecDecodeOnStore) && !PAIRS && out != nullptr) {
+    } else if (full && !dec && !PAIRS && out != nullptr) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;
             const KeyT k = sm.sorted[idx];
-            st_stream(out + static_cast<uint32_t>(sm.off32[digit_of(k, shift)] + idx), k);
+            st_stream(out + static_cast<uint32_t>(sm.off32[digit_of(k, shift, dmask)] + idx), k);
         }
 #endif
-    } else if (full && !(codec.flags & kCodecDecodeOnStore)) {  // branch-free: all shared loads of the unrolled body in flight together
+#if OSB_ABL & 16
+    } else if (full && !dec) {
+#endif
+#if !(OSB_ABL & 16)
+    } else if (full && !dec) {  // branch-free: all shared loads of the unrolled body in flight together
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;
             const KeyT k = sm.sorted[idx];
-            const uint32_t d = digit_of(k, shift);
+            const uint32_t d = digit_of(k, shift, dmask);
+#if OSB_ABL & 2
+            KeyT* dst = reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx;
+            asm volatile("" ::"l"(dst), "l"(static_cast<unsigned long long>(k)) : "memory");  // pointer math and LDS stay, the store does not
+#else
             st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
+#endif
             if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
         }
+#endif
     } else {  // ragged last tile, or the last pass of a typed sort (keys leave decoded)
-        const bool dec = codec.flags & kCodecDecodeOnStore;
-        const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
 #pragma unroll 4
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;
             if (idx < valid) {
                 const KeyT k = sm.sorted[idx];
-                const uint32_t d = digit_of(k, shift);
+                const uint32_t d = digit_of(k, shift, dmask);
                 st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, dec ? codec_decode<KeyT>(k, ca, cb, cd) : k);
                 if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
             }
@@ -926,7 +1085,10 @@ digit_binning_ring_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, u
         for (int i = 0; i < K; ++i) s_keys[warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift), lt)] = key[i];
 
         if (tid < kRadix) {
-            const unsigned long long prior = lookback_wide<LOOK, STEP>(agg16, incl64, tile, tid, epoch);
+            TileRereduce<KeyT> rr;
+            rr.in = in; rr.tile_keys = T; rr.shift = shift; rr.mask = kRadix - 1; rr.encode = false;
+            rr.ca = rr.cb = rr.cd = 0;
+            const unsigned long long prior = lookback_wide<LOOK, STEP, KeyT>(agg16, incl64, tile, tid, epoch, 1u << 20, rr);
             st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
                                desc_pack(epoch, kFlagInclusive, prior + tile_count));
             sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + (gbase[tid] + prior - tile_excl) * sizeof(KeyT);
@@ -1014,15 +1176,24 @@ template <> struct WideGeom<uint64_t, false> { static constexpr int K = 16, WARP
 template <typename KeyT, bool PAIRS, int RANK_MODE>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
                                        uint32_t shift, const unsigned long long* gbase, uint16_t* agg16, uint64_t* incl64,
-                                       uint32_t* ticket, uint32_t epoch, const KeyCodec& codec, cudaStream_t stream)
+                                       uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg, cudaStream_t stream)
 {
     using G = WideGeom<KeyT, PAIRS>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
     const uint64_t tiles = (n + S::T - 1) / S::T;
+    PassParams pp;
+    pp.shift = shift;
+    pp.dbits = cfg.digit_bits;
+    pp.epoch = epoch;
+    pp.place = cfg.place;
+    pp.spin_cap = cfg.spin_cap;
+    pp.stall_every = cfg.debug_stall_every;
+    pp.plan = cfg.plan;
     auto kern = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>;
+    // with a device plan `in`/`out` are the caller's and the alt buffers (the kernel picks the direction); both are written
     kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
-        static_cast<const KeyT*>(in), static_cast<KeyT*>(out), in_val, out_val, n, shift, gbase, agg16, incl64, ticket, epoch,
-        codec);
+        static_cast<KeyT*>(const_cast<void*>(in)), static_cast<KeyT*>(out), const_cast<uint32_t*>(in_val), out_val, n, gbase,
+        agg16, incl64, ticket, pp, cfg.codec);
     return cudaGetLastError();
 }
 
@@ -1094,6 +1265,10 @@ cudaError_t configure_kernels()
                                   static_cast<int>(hist_smem_bytes<uint32_t>()))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(global_histogram_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(hist_smem_bytes<uint64_t>()))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(global_histogram_bits_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(hist_smem_bytes<uint32_t>()))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(global_histogram_bits_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(hist_smem_bytes<uint64_t>()))) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint32_t, false, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint32_t, false, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_tile_attr<uint32_t, true, kRankAtomic>()) != cudaSuccess) return e;
@@ -1120,13 +1295,17 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
 {
     const bool pairs = in_val != nullptr;
     const bool ballot = cfg.rank_mode == kRankBallot;
-    if (cfg.codec.flags && cfg.variant != kVariantWide) return cudaErrorNotSupported;  // typed keys: default kernel only
+    if (cfg.variant != kVariantWide && (cfg.codec.flags || cfg.plan != nullptr || cfg.debug_stall_every)) return cudaErrorNotSupported;
+    if (cfg.digit_bits < 1 || cfg.digit_bits > 8) return cudaErrorInvalidValue;
+    // variants 0 and 1 always take 8-bit digits: a narrower digit is only correct for them when the bits above it do not exist
+    if (cfg.variant != kVariantWide && cfg.digit_bits != 8 && shift + cfg.digit_bits != static_cast<uint32_t>(key_bytes) * 8u)
+        return cudaErrorNotSupported;
     if (cfg.variant == kVariantWide) {
 #define OSB_WIDE(KEYT, PAIRS)                                                                                          \
     (ballot ? launch_wide_variant<KEYT, PAIRS, kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
-                                                           ticket, epoch, cfg.codec, stream)                           \
+                                                           ticket, epoch, cfg, stream)                                 \
             : launch_wide_variant<KEYT, PAIRS, kRankAtomic>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
-                                                           ticket, epoch, cfg.codec, stream))
+                                                           ticket, epoch, cfg, stream))
         if (key_bytes == 4) return pairs ? OSB_WIDE(uint32_t, true) : OSB_WIDE(uint32_t, false);
         if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false);
 #undef OSB_WIDE
@@ -1218,29 +1397,48 @@ cudaError_t launch_init_random(uint32_t* keys, uint32_t* payload, uint64_t n, ui
 // =====================================================================================================
 // Self-test of the hardware property RankMode::kRankAtomic relies on
 // =====================================================================================================
-__global__ void __launch_bounds__(256)
+// Production geometry on purpose: 512 threads = 16 warps with a 256-bin histogram each, two CTAs per SM, batches of 16
+// back-to-back returning atomics per thread interleaved with data-dependent shared-memory stores (the rank phase of
+// digit_binning_wide_kernel), digits from uniform down to "every lane the same".  The ballot formulation on a second
+// histogram is the reference answer.
+constexpr int kSelfTestWarps = 16;
+__global__ void __launch_bounds__(kSelfTestWarps * 32, 2)
 atomic_order_selftest_kernel(unsigned long long* mismatches)
 {
-    __shared__ uint32_t s_hist[8 * kRadix];
-    __shared__ uint32_t s_ref[8 * kRadix];
+    __shared__ uint32_t s_hist[kSelfTestWarps * kRadix];
+    __shared__ uint32_t s_ref[kSelfTestWarps * kRadix];
+    __shared__ uint32_t s_scratch[kSelfTestWarps * 32 * 4];  // stands in for the sorted tile: random-bank STS traffic
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* wh = s_hist + warp * kRadix;
     uint32_t* wr = s_ref + warp * kRadix;
-    uint32_t s = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
     const uint32_t lt = lanemask_lt();
     unsigned long long bad = 0;
+    constexpr int B = 16;
     for (int it = 0; it < 24; ++it) {
         for (int i = lane; i < kRadix; i += 32) { wh[i] = 0; wr[i] = 0; }
         __syncwarp();
-        for (int i = 0; i < 16; ++i) {
-            uint32_t d = 255u;
-            const int draws = 1 + (it % 6);  // entropy sweep: uniform digits down to heavy collisions
-            for (int k = 0; k < draws; ++k) { s = s * 1664525u + 1013904223u; d &= (s >> 13); }
-            if (it % 6 == 5) d = (it + i) & 255u;  // every lane the same digit
-            const uint32_t got = warp_rank_and_count<kRankAtomic>(wh, d, lt);
-            const uint32_t want = warp_rank_and_count<kRankBallot>(wr, d, lt);
-            bad += (got != want);
-            __syncwarp();
+        for (int batch = 0; batch < 2; ++batch) {
+            uint32_t d[B], got[B];
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                uint32_t x = 255u;
+                const int draws = 1 + (it % 6);  // entropy sweep: uniform digits down to heavy collisions
+                for (int k = 0; k < draws; ++k) { s = s * 1664525u + 1013904223u; x &= (s >> 13); }
+                if (it % 6 == 5) x = (it + i) & 255u;  // every lane the same digit
+                d[i] = x;
+            }
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                got[i] = warp_rank_and_count<kRankAtomic>(wh, d[i], lt);
+                s_scratch[(got[i] * 37u + d[i] * 5u + threadIdx.x) & (kSelfTestWarps * 32 * 4 - 1)] = d[i];
+            }
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                const uint32_t want = warp_rank_and_count<kRankBallot>(wr, d[i], lt);
+                bad += (got[i] != want);
+                __syncwarp();
+            }
         }
     }
     if (bad) atomicAdd(mismatches, bad);
@@ -1248,7 +1446,7 @@ atomic_order_selftest_kernel(unsigned long long* mismatches)
 
 cudaError_t launch_atomic_order_selftest(unsigned long long* mismatches, int sm_count, cudaStream_t stream)
 {
-    atomic_order_selftest_kernel<<<sm_count * 2, 256, 0, stream>>>(mismatches);
+    atomic_order_selftest_kernel<<<sm_count * 2, kSelfTestWarps * 32, 0, stream>>>(mismatches);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,12 @@ struct BinningConfig {
     int rank_mode = kRankAtomic;
     int sm_count = 148;
     KeyCodec codec;  // typed keys: encode-on-load / decode-on-store for THIS launch (flags 0 = plain unsigned keys)
+    // --- per-launch pass parameters (kVariantWide honours all of them; the other variants need the defaults) ---
+    uint32_t digit_bits = 8;          // width of this pass's digit, 1..8 (narrower: last place of a begin/end-bit sort)
+    const SortPlan* plan = nullptr;   // device plan: skip flag, ping-pong parity, dynamic codec flags; null = as launched
+    uint32_t place = 0;               // index of this pass in the plan
+    uint32_t spin_cap = 2048;         // lookback polls of one predecessor before the digit thread re-reduces that tile itself
+    uint32_t debug_stall_every = 0;   // test hook: tiles with tile % N == N-1 never publish their reduction (0 = off)
 };
 
 // keys per partition tile for a key width / pairs flag / variant (host needs it to size descriptors)
@@ -42,7 +48,20 @@ cudaError_t launch_digit_histogram(const void* keys, uint64_t n, int key_bytes, 
                                    unsigned long long* hist256, int sm_count, cudaStream_t stream);
 
 // Scan (reference: OneSweep::Scan, Sort/OneSweep.cu:125-162): per place exclusive prefix of ghist -> gbase.
-cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream);
+// With plan != null the kernel also writes the device launch plan: a place is skipped when one of its bins holds all n
+// keys (allow_skip), and the first/last executed places are recorded for the typed-key codec.
+cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream,
+                        SortPlan* plan = nullptr, uint64_t n = 0, bool allow_skip = false);
+
+// GlobalHistogram of a begin_bit/end_bit sort: place p counts the digit (key >> (begin_bit + 8p)) & mask_p, mask_p = 255
+// except for the last place, which keeps last_bits bits.  (The byte-aligned full-width case uses launch_global_histogram.)
+cudaError_t launch_global_histogram_bits(const void* keys, uint64_t n, int key_bytes, unsigned long long* ghist, int sm_count,
+                                         cudaStream_t stream, const KeyCodec* codec, uint32_t begin_bit, int places,
+                                         uint32_t last_bits);
+
+// If the plan says an odd number of passes ran, the sorted data sits in the alt buffers: move it to the caller's.
+cudaError_t launch_copy_back(const SortPlan* plan, const void* alt_keys, void* keys, const uint32_t* alt_vals, uint32_t* vals,
+                             uint64_t n, int key_bytes, int sm_count, cudaStream_t stream);
 
 // DigitBinningPass (reference: OneSweep::DigitBinningPassKeysOnly / Pairs, Sort/OneSweep.cu:164-600).
 //   gbase_place: [256] exclusive global digit bases for this digit place

@@ -138,6 +138,18 @@ class OneSweepSorter:
                                               1 if descending else 0, _stream_ptr(stream)), "osb200_sort_pairs_typed")
         return keys, values
 
+    def sort_bits(self, keys: torch.Tensor, begin_bit: int, end_bit: int, values: Optional[torch.Tensor] = None,
+                  n: Optional[int] = None, stream=None):
+        """Stable sort on the key bits [begin_bit, end_bit) only (osb200_sort_bits)."""
+        n = keys.numel() if n is None else int(n)
+        _check_dev_tensor(keys, self._raw(), "keys", n, self.device)
+        if values is not None:
+            _check_dev_tensor(values, _TYPED_DTYPES_4, "values", n, self.device)
+        with torch.cuda.device(self.device):
+            check(lib.osb200_sort_bits(self._h, keys.data_ptr(), values.data_ptr() if values is not None else None, n,
+                                       int(begin_bit), int(end_bit), _stream_ptr(stream)), "osb200_sort_bits")
+        return keys if values is None else (keys, values)
+
     def sort_pairs(self, keys: torch.Tensor, values: torch.Tensor, n: Optional[int] = None, stream=None):
         n = keys.numel() if n is None else int(n)
         _check_dev_tensor(keys, _KEY_DTYPES_4, "keys", n, self.device)

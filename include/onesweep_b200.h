@@ -97,6 +97,14 @@ OSB200_API int osb200_sort_keys_typed(osb200_handle h, void* d_keys, uint64_t n,
 OSB200_API int osb200_sort_pairs_typed(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int key_type,
                                        int descending, void* stream);
 
+/* Sort on a bit range [begin_bit, end_bit) of the (unsigned) key only, CUB-style: keys that agree on those bits keep their
+ * input order (stable).  ceil((end_bit-begin_bit)/8) digit passes instead of key_bytes; the last digit may be narrower
+ * than 8 bits; an odd pass count is handled inside (the result is always returned in the caller's buffers).  d_values may
+ * be NULL (keys only).  begin_bit == end_bit is a no-op.  Reference: none in CUDA (its passes are fixed at radixShift
+ * 0/8/16/24, Sort/OneSweepDispatcher.cuh:325-335); SURVEY 8f rank 2. */
+OSB200_API int osb200_sort_bits(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int begin_bit, int end_bit,
+                                void* stream);
+
 /* Host-buffer entry points: copy in, sort, copy back, synchronise.  `h_*` may be pageable or pinned
  * host memory.  This is the end-to-end call a host-side caller of the reference would make (the
  * reference itself has no host-data API; its buffers are generated on the device,
@@ -132,8 +140,23 @@ OSB200_API int osb200_init_random_u32(uint32_t* d_keys, uint32_t* d_payload, uin
                            int payload_is_index, void* stream);
 
 /* Tuning / introspection (no reference equivalent; the reference's constants are #defines,
- * Sort/OneSweep.cu:17-42).  Keys: "rank_mode" 0=atomic-ranked (default) 1=ballot-ranked;
- * "variant" kernel variant id; returns OSB200_ERR_INVALID_ARG for unknown keys/values. */
+ * Sort/OneSweep.cu:17-42).  Returns OSB200_ERR_INVALID_ARG for unknown keys/values.  Options:
+ *   "rank_mode"      0 = atomic-ranked (default), 1 = ballot-ranked.  The default ranks keys with ONE shared-memory
+ *                    atomicAdd per key and relies on sm_100 handing the return values of one warp-wide ATOMS.ADD to
+ *                    same-address lanes in ascending lane order -- an UNDOCUMENTED hardware property on which the
+ *                    stability of every pass rests.  osb200_create verifies it on the device (a self-test kernel in the
+ *                    production geometry) and falls back to 1 if it ever fails; 1 is the supported escape hatch: it uses
+ *                    the reference's documented 8-ballot warp multisplit (Sort/OneSweep.cu:208-253) at ~2x the pass time.
+ *   "variant"        kernel variant id (2 = default wide-tile kernel; 0/1 development baselines)
+ *   "short_circuit"  1 (default) = digit passes on which ALL keys agree are skipped, decided on the device from the
+ *                    global histogram without any host synchronisation; 0 = always run every pass like the reference
+ *   "spin_cap"       lookback polls of one predecessor tile before a digit thread stops waiting and re-reduces that
+ *                    tile itself (forward-progress fallback, reference: Sort/EmulatedDeadlocking.cu:159-267)
+ *   "debug_stall_every"  test hook for that fallback: N > 0 makes every N-th tile withhold its reduction
+ *   "profile"        1 = record CUDA events between the kernels of a sort (osb200_get_profile)
+ * Info keys: "tile_keys","launches_per_sort","memsets_per_sort","sm_count","rank_mode","variant","atomic_order_ok",
+ * "max_n","epoch","short_circuit","spin_cap","last_skip_mask","last_executed_passes" (the last two read the device plan
+ * of the previous sort and synchronise). */
 OSB200_API int osb200_set_option(osb200_handle h, const char* key, int64_t value);
 OSB200_API int64_t osb200_get_info(osb200_handle h, const char* key);
 /* With option "profile"=1 every sort records CUDA events on its stream between its kernels.  Returns the number of

@@ -278,9 +278,13 @@ def test_host_buffer_entry_points(g, oracle):
 
 def test_error_behaviour(g, sorter):
     t = torch.zeros(16, dtype=torch.int32, device="cuda")
+    small = g.OneSweepSorter(1024, 4, 0)
     with pytest.raises(g.OneSweepError) as e:
-        sorter.sort_keys(t, (1 << 22) + 1)  # n > max_n
+        small.sort_keys(torch.zeros(2048, dtype=torch.int32, device="cuda"))  # n > max_n
     assert e.value.status == -2
+    small.close()
+    with pytest.raises(ValueError):  # n beyond the tensor
+        sorter.sort_keys(t, 17)
     with pytest.raises(g.OneSweepError):  # misaligned keys
         sorter.sort_keys(t[1:], 8)
     with pytest.raises(TypeError):
