@@ -607,19 +607,20 @@ struct TileRereduce {
 // has spun too long on a predecessor's flag stops waiting and computes that tile's reduction itself).  Here every digit
 // thread that gives up on tile x counts ITS digit over the tile's keys (the whole warp reads the same key: one
 // broadcast transaction per load; predecessor tiles are never the ragged last tile) and publishes the reduction on the
-// owner's behalf -- the value is the one the owner would write, so concurrent publishers agree.
+// owner's behalf -- the value is the one the owner would write, so concurrent publishers agree.  Cold path, kept out of
+// line (scalar arguments: nothing of the caller's goes through the stack).
 template <typename KeyT>
-__device__ __noinline__ uint32_t rereduce_tile(const TileRereduce<KeyT>& rr, uint16_t* agg16, int64_t x, uint32_t d)
+__device__ __noinline__ uint32_t rereduce_tile(const KeyT* p, uint32_t tile_keys, uint32_t shift, uint32_t mask, uint32_t encode,
+                                               KeyT ca, KeyT cb, KeyT cd, uint16_t* dst, uint32_t d)
 {
-    const KeyT* p = rr.in + static_cast<uint64_t>(x) * rr.tile_keys;
     uint32_t c = 0;
 #pragma unroll 8
-    for (uint32_t i = 0; i < rr.tile_keys; ++i) {
+    for (uint32_t i = 0; i < tile_keys; ++i) {
         KeyT k = p[i];
-        if (rr.encode) k = codec_encode<KeyT>(k, rr.ca, rr.cb, rr.cd);
-        c += digit_of(k, rr.shift, rr.mask) == d;
+        if (encode) k = codec_encode<KeyT>(k, ca, cb, cd);
+        c += digit_of(k, shift, mask) == d;
     }
-    st_relaxed_gpu_u16(agg16 + x * kRadix + d, kAggReady | c);
+    st_relaxed_gpu_u16(dst, kAggReady | c);
     return c;
 }
 
@@ -672,7 +673,8 @@ lookback_wide(uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d
                 // maybe the stalled tile has finished altogether meanwhile: its inclusive prefix settles everything
                 const uint64_t v = ld_relaxed_gpu_u64(incl64 + next * kRadix + d);
                 if (desc_epoch(v) == epoch && (v & kFlagMask) == kFlagInclusive) return sum + desc_value(v);
-                sum += rereduce_tile<KeyT>(rr, agg16, next, d);
+                sum += rereduce_tile<KeyT>(rr.in + static_cast<uint64_t>(next) * rr.tile_keys, rr.tile_keys, rr.shift, rr.mask,
+                                           rr.encode ? 1u : 0u, rr.ca, rr.cb, rr.cd, agg16 + next * kRadix + d, d);
                 --next;
                 polls = 0;
             } else {
@@ -756,6 +758,9 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     if (tid == 0) {
         // The device plan (if any) decides whether this pass runs at all, which buffer it reads, and -- typed keys --
         // whether it is the pass that encodes / decodes.  Without a plan the launch arguments are taken as they are.
+        // the ticket is drawn first and unconditionally, so that its L2 round trip overlaps the plan's (a skipped pass
+        // wastes a ticket nobody reads)
+        const uint32_t drawn = atomicAdd(ticket, 1u);  // dynamic tile id: predecessors are already scheduled
         uint32_t bits = (codec.flags & (kCodecEncodeOnLoad | kCodecDecodeOnStore)) << 1;
         bool skip = false;
         if (pp.plan != nullptr) {
@@ -766,7 +771,7 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
                 bits |= (pp.place == pl.first_exec ? kCodecEncodeOnLoad << 1 : 0u) | (pp.place == pl.last_exec ? kCodecDecodeOnStore << 1 : 0u);
         }
         sm.plan_bits = bits;
-        const uint32_t t = skip ? 0xffffffffu : atomicAdd(ticket, 1u);  // dynamic tile id: predecessors are already scheduled
+        const uint32_t t = skip ? 0xffffffffu : drawn;
         sm.tile = t;
 #if OSB_EXP & 8
         mbar_init(&sm.bar, 1);
@@ -781,14 +786,8 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     __syncthreads();
     const uint32_t tile = sm.tile;
     if (tile == 0xffffffffu) return;  // all keys share this digit: nothing to move (the plan accounts for the parity)
-    const uint32_t plan_bits = sm.plan_bits;
-    const bool swap = plan_bits & 1u;
-    const uint32_t cflags = plan_bits >> 1;
-    const KeyT* __restrict__ in = swap ? buf1 : buf0;
-    KeyT* __restrict__ out = swap ? buf0 : buf1;
-    const uint32_t* __restrict__ in_val = swap ? val1 : val0;
-    uint32_t* __restrict__ out_val = swap ? val0 : val1;
-
+    // plan_bits (direction, codec flags) is re-read from shared memory where it is needed instead of being carried in
+    // registers across the phases: the 64-register budget of this kernel is spent on the 32 keys and their counter addresses
     const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
     const bool full = tile_base + T <= n;
     const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
@@ -797,6 +796,10 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     KeyT key[K];
     uint32_t val[PAIRS ? K : 1];
     const uint32_t warp_off = warp * (32 * K) + lane;
+    {
+    const bool swap = sm.plan_bits & 1u;
+    const KeyT* __restrict__ in = swap ? buf1 : buf0;
+    const uint32_t* __restrict__ in_val = swap ? val1 : val0;
     if (full) {
 #if OSB_EXP & 8
         mbar_wait(&sm.bar, 0);
@@ -818,12 +821,13 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
             if constexpr (PAIRS) val[i] = idx < valid ? in_val[tile_base + idx] : 0u;
         }
     }
+    }
 
     // typed keys: the first executed pass of a sort turns the caller's keys into order-equivalent unsigned keys.  The
     // padding of the ragged last tile is encoded too and stays the largest key only if it was loaded as the pre-image of
     // all-ones, so it is simply re-set after encoding.
-    const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
-    if (cflags & kCodecEncodeOnLoad) {
+    if ((sm.plan_bits >> 1) & kCodecEncodeOnLoad) {
+        const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
 #pragma unroll
         for (int i = 0; i < K; ++i) {
             key[i] = codec_encode<KeyT>(key[i], ca, cb, cd);
@@ -862,10 +866,14 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
             const unsigned long long prior = static_cast<unsigned long long>(tile) * (T / kRadix - 4);  // ~uniform input: realistic addresses, in bounds
 #else
             TileRereduce<KeyT> rr;
-            rr.in = in; rr.tile_keys = T; rr.shift = shift; rr.mask = dmask;
-            rr.encode = cflags & kCodecEncodeOnLoad; rr.ca = ca; rr.cb = cb; rr.cd = cd;
+            rr.in = (sm.plan_bits & 1u) ? buf1 : buf0; rr.tile_keys = T; rr.shift = shift; rr.mask = dmask;
+            rr.encode = (sm.plan_bits >> 1) & kCodecEncodeOnLoad;
+            rr.ca = static_cast<KeyT>(codec.a); rr.cb = static_cast<KeyT>(codec.b); rr.cd = static_cast<KeyT>(codec.d);
             const unsigned long long prior = lookback_wide<LOOK, STEP, KeyT>(agg16, incl64, tile, tid, epoch, pp.spin_cap, rr);
 #endif
+            const bool swap = sm.plan_bits & 1u;
+            KeyT* out = swap ? buf0 : buf1;
+            uint32_t* out_val = swap ? val0 : val1;
             st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
                                desc_pack(epoch, kFlagInclusive, prior + tile_count));
             const unsigned long long first = gbase[tid] + prior - tile_excl;  // element index (relative to out) of tile slot 0
@@ -891,7 +899,7 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     // below re-derives it from the tile, so the decoded form is produced only at the very end, in the store)
 #if OSB_ABL & 8
 #pragma unroll
-    for (int i = 0; i < K; ++i) asm volatile("" ::"l"(static_cast<unsigned long long>(key[i])) : "memory");  // keep the loads live
+    for (int i = 0; i < K; ++i) asm volatile("" ::"l"(static_cast<unsigned long long>(key[i])));  // keep the loads live
 #else
 #pragma unroll
     for (int i = 0; i < K; ++i) {
@@ -911,7 +919,8 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     // the stores are issued run by run in chunks that start on 128-byte boundaries of the DESTINATION -- every warp
     // store is then one full line (4 full sectors), which is what keeps NVLink peer stores at their aligned rate
     // (profiles/r01_p2p_store_ub.txt: 128-B aligned 680-716 GB/s vs 390-580 GB/s at 4-byte alignment).
-    const bool dec = cflags & kCodecDecodeOnStore;
+    const bool dec = (sm.plan_bits >> 1) & kCodecDecodeOnStore;
+    const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
     if (pp.dbits <= 5) {
         const uint32_t nbins = 1u << pp.dbits;
         for (uint32_t b = 0; b < nbins; ++b) {
@@ -933,7 +942,8 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
             }
         }
 #if OSB_EXP & 1
-    } else if (full && !dec && !PAIRS && out != nullptr) {
+    } else if (full && !dec && !PAIRS && ((sm.plan_bits & 1u) ? buf0 : buf1) != nullptr) {
+        KeyT* out = (sm.plan_bits & 1u) ? buf0 : buf1;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;
@@ -953,7 +963,7 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
             const uint32_t d = digit_of(k, shift, dmask);
 #if OSB_ABL & 2
             KeyT* dst = reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx;
-            asm volatile("" ::"l"(dst), "l"(static_cast<unsigned long long>(k)) : "memory");  // pointer math and LDS stay, the store does not
+            asm volatile("" ::"l"(dst), "l"(static_cast<unsigned long long>(k)));  // pointer math and LDS stay, the store does not
 #else
             st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
 #endif
@@ -996,8 +1006,16 @@ struct RingSmem {
     uint32_t wtot[kRadix / 32];
 };
 
+#ifndef OSB_LOOK  // overridable for parameter sweeps (tools/sweep.sh)
+#define OSB_LOOK 8
+#define OSB_STEP 4
+#endif
+#ifndef OSB_RING_K  // u32 geometry of the ring kernel, overridable for sweeps: keys per thread, resident CTAs per SM
+#define OSB_RING_K 16
+#define OSB_RING_MINB 2
+#endif
 template <typename KeyT, int K, int WARPS, int RANK_MODE, int LOOK, int STEP>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+__global__ void __launch_bounds__(WARPS * 32, (sizeof(KeyT) == 4 ? OSB_RING_MINB : 2))
 digit_binning_ring_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, uint64_t n, uint32_t shift,
                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
                           uint32_t* ticket, uint32_t epoch, uint32_t num_tiles)
@@ -1124,7 +1142,7 @@ digit_binning_ring_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, u
 }
 
 template <typename KeyT> struct RingGeom;
-template <> struct RingGeom<uint32_t> { static constexpr int K = 16, WARPS = 16, LOOK = 16, STEP = 8; };
+template <> struct RingGeom<uint32_t> { static constexpr int K = OSB_RING_K, WARPS = 16, LOOK = OSB_LOOK, STEP = OSB_STEP; };
 template <> struct RingGeom<uint64_t> { static constexpr int K = 8,  WARPS = 16, LOOK = 16, STEP = 8; };
 
 template <typename KeyT, int RANK_MODE>
@@ -1135,7 +1153,7 @@ static cudaError_t launch_ring_variant(const void* in, void* out, uint64_t n, ui
     using G = RingGeom<KeyT>;
     using S = RingSmem<KeyT, G::K, G::WARPS>;
     const uint64_t tiles = (n + S::T - 1) / S::T;
-    const uint64_t cap = static_cast<uint64_t>(sm_count) * 2;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * (sizeof(KeyT) == 4 ? OSB_RING_MINB : 2);
     const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
     auto kern = digit_binning_ring_kernel<KeyT, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP>;
     kern<<<grid, S::THREADS, sizeof(S), stream>>>(static_cast<const KeyT*>(in), static_cast<KeyT*>(out), n, shift, gbase, agg16,
@@ -1159,10 +1177,6 @@ static cudaError_t set_ring_attr()
 // 8,192-key tiles on 4 x 256 threads 2.89.  Every geometry that avoids spills lands on the same ~2.73 ms: the pass is
 // bound by the number of L1/shared-memory wavefronts per key, not by occupancy.  Lookback window/probe spacing (whole
 // sort, ms): 8/4 11.71, 8/2 11.78, 8/8 11.77, 4/2 11.82, 4/4 11.89, 16/4 11.89, 16/8 11.97, 24/8 12.06, 2/2 12.38, 32/8 12.99.
-#ifndef OSB_LOOK  // overridable for parameter sweeps (tools/sweep.sh)
-#define OSB_LOOK 8
-#define OSB_STEP 4
-#endif
 template <typename KeyT, bool PAIRS> struct WideGeom;
 #ifndef OSB_WIDE_WARPS  // geometry of the u32 keys-only kernel, overridable for sweeps
 #define OSB_WIDE_WARPS 16
@@ -1407,7 +1421,7 @@ atomic_order_selftest_kernel(unsigned long long* mismatches)
 {
     __shared__ uint32_t s_hist[kSelfTestWarps * kRadix];
     __shared__ uint32_t s_ref[kSelfTestWarps * kRadix];
-    __shared__ uint32_t s_scratch[kSelfTestWarps * 32 * 4];  // stands in for the sorted tile: random-bank STS traffic
+    __shared__ volatile uint32_t s_scratch[kSelfTestWarps * 32 * 4];  // stands in for the sorted tile: random-bank STS traffic
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* wh = s_hist + warp * kRadix;
     uint32_t* wr = s_ref + warp * kRadix;
