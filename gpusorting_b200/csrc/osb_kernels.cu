@@ -985,6 +985,208 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
 }
 
 // =====================================================================================================
+// DigitBinningPass for (uint32 key, uint32 payload) pairs: 16,384-PAIR tiles (reference: OneSweep::DigitBinningPassPairs,
+// OneSweep.cu:346-600, which like this kernel moves the payloads after the keys, through the same shared memory).
+//
+// The pairs instantiation of the kernel above holds keys AND payloads in registers and therefore stops at 8,192-pair
+// tiles: twice the tiles, twice the per-tile work (ticket, histogram clear/reduce, chained scan, barriers) per pair.
+// Here a tile is as large as for keys: the keys are ranked and scattered first; each thread remembers the tile slots
+// of its 32 keys (14 bits each, two per register); the payloads are loaded into the registers the keys have left (the
+// loads fly during the chained scan and the key scatter), go through the SAME 64 KB buffer at the remembered slots, and
+// are scattered with the digit the key scatter has noted per slot (one byte).  100 KB of shared memory, two CTAs per SM.
+// =====================================================================================================
+#ifndef OSB_PAIRS16K
+#define OSB_PAIRS16K 1
+#endif
+template <int WARPS, int K>
+struct PairsSmem {
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int T = THREADS * K;
+    alignas(16) uint32_t sorted[T];            // digit-sorted keys, later the payloads in the same order
+    alignas(16) uint32_t hist[WARPS * kRadix];
+    unsigned long long keyptr[kRadix];
+    unsigned long long valptr[kRadix];
+    alignas(16) unsigned char dig[T];          // digit of every tile slot (written by the key scatter)
+    uint32_t wtot[kRadix / 32];
+    uint32_t tile;
+    uint32_t plan_bits;
+};
+
+template <int K, int WARPS, int RANK_MODE, int LOOK, int STEP>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+digit_binning_pairs_kernel(uint32_t* buf0, uint32_t* buf1, uint32_t* val0, uint32_t* val1, uint64_t n,
+                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
+                           uint32_t* ticket, PassParams pp, KeyCodec codec)
+{
+    using KeyT = uint32_t;
+    using S = PairsSmem<WARPS, K>;
+    constexpr int THREADS = S::THREADS;
+    constexpr int T = S::T;
+    static_assert(T <= 16384 && (K % 2) == 0, "slots are kept as 14-bit halves of a register");
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    S& sm = *reinterpret_cast<S*>(s_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    uint32_t* wh = sm.hist + warp * kRadix;
+    const uint32_t shift = pp.shift, epoch = pp.epoch;
+    const uint32_t dmask = (1u << pp.dbits) - 1u;
+
+    {
+        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+        for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tid == 0) {
+        const uint32_t drawn = atomicAdd(ticket, 1u);
+        uint32_t bits = (codec.flags & (kCodecEncodeOnLoad | kCodecDecodeOnStore)) << 1;
+        bool skip = false;
+        if (pp.plan != nullptr) {
+            const SortPlan pl = *pp.plan;
+            skip = (pl.skip_mask >> pp.place) & 1u;
+            bits = plan_src_is_alt(pl, pp.place) ? 1u : 0u;
+            if (codec.flags & kCodecFromPlan)
+                bits |= (pp.place == pl.first_exec ? kCodecEncodeOnLoad << 1 : 0u) | (pp.place == pl.last_exec ? kCodecDecodeOnStore << 1 : 0u);
+        }
+        sm.plan_bits = bits;
+        sm.tile = skip ? 0xffffffffu : drawn;
+    }
+    __syncthreads();
+    const uint32_t tile = sm.tile;
+    if (tile == 0xffffffffu) return;
+    const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
+    const bool full = tile_base + T <= n;
+    const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
+    const uint32_t warp_off = warp * (32 * K) + lane;
+
+    // ---- keys ---------------------------------------------------------------------------------------------
+    uint32_t key[K];  // later: the payloads
+    {
+        const KeyT* __restrict__ in = (sm.plan_bits & 1u) ? buf1 : buf0;
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) key[i] = ld_stream(in + tile_base + warp_off + i * 32);
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t idx = warp_off + i * 32;
+                key[i] = idx < valid ? in[tile_base + idx] : 0xffffffffu;  // pad: ranks last
+            }
+        }
+    }
+    if ((sm.plan_bits >> 1) & kCodecEncodeOnLoad) {
+        const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            key[i] = codec_encode<KeyT>(key[i], ca, cb, cd);
+            if (!full && warp_off + i * 32 >= valid) key[i] = 0xffffffffu;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift, dmask)], 1u);
+    __syncthreads();
+
+    uint32_t tile_count = 0, tile_excl = 0;
+    if (tid < kRadix) {
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
+        if (pp.stall_every == 0 || (tile % pp.stall_every) != pp.stall_every - 1)
+            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+    }
+    tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
+    if (tid < kRadix) {
+        uint32_t run = tile_excl;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
+    }
+    __syncthreads();
+
+    // ---- chained scan, BEFORE the rank phase: the digit warps look back while the other warps already rank, and no
+    // lookback state competes with the remembered slots for registers later on ------------------------------------
+    if (tid < kRadix) {
+        TileRereduce<KeyT> rr;
+        rr.in = (sm.plan_bits & 1u) ? buf1 : buf0; rr.tile_keys = T; rr.shift = shift; rr.mask = dmask;
+        rr.encode = (sm.plan_bits >> 1) & kCodecEncodeOnLoad;
+        rr.ca = static_cast<KeyT>(codec.a); rr.cb = static_cast<KeyT>(codec.b); rr.cd = static_cast<KeyT>(codec.d);
+        const unsigned long long prior = lookback_wide<LOOK, STEP, KeyT>(agg16, incl64, tile, tid, epoch, pp.spin_cap, rr);
+        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid, desc_pack(epoch, kFlagInclusive, prior + tile_count));
+        const bool swap = sm.plan_bits & 1u;
+        const unsigned long long first = gbase[tid] + prior - tile_excl;
+        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(swap ? buf0 : buf1) + first * sizeof(KeyT);
+        sm.valptr[tid] = reinterpret_cast<unsigned long long>(swap ? val0 : val1) + first * sizeof(uint32_t);
+    }
+    // ---- rank: keys to their slots; the slots are kept for the payloads --------------------------------------
+    uint32_t slots[K / 2];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift, dmask), lt);
+        sm.sorted[slot] = key[i];
+        if (i & 1) slots[i / 2] |= slot << 16; else slots[i / 2] = slot;
+    }
+    __syncthreads();
+
+    // ---- payloads: loaded into the registers the keys have left; in flight during the key scatter (issued after the
+    // chained scan, whose lookback needs the registers)
+    asm volatile("" ::: "memory");
+    {
+        const uint32_t* __restrict__ in_val = (sm.plan_bits & 1u) ? val1 : val0;
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) key[i] = ld_stream(in_val + tile_base + warp_off + i * 32);
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t idx = warp_off + i * 32;
+                key[i] = idx < valid ? in_val[tile_base + idx] : 0u;
+            }
+        }
+    }
+
+    // ---- key scatter (notes the digit of every slot for the payload scatter) ---------------------------------
+    {
+        const bool dec = (sm.plan_bits >> 1) & kCodecDecodeOnStore;
+        const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
+        if (full && !dec) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const uint32_t idx = j * THREADS + tid;
+                const KeyT k = sm.sorted[idx];
+                const uint32_t d = digit_of(k, shift, dmask);
+                sm.dig[idx] = static_cast<unsigned char>(d);
+                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < K; ++j) {
+                const uint32_t idx = j * THREADS + tid;
+                const KeyT k = sm.sorted[idx];
+                const uint32_t d = digit_of(k, shift, dmask);
+                sm.dig[idx] = static_cast<unsigned char>(d);
+                if (idx < valid) st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, dec ? codec_decode<KeyT>(k, ca, cb, cd) : k);
+            }
+        }
+    }
+    __syncthreads();  // every key has left the buffer
+
+    // ---- payloads through the same buffer ---------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < K; ++i) sm.sorted[(slots[i / 2] >> (16 * (i & 1))) & 0xffffu] = key[i];
+    __syncthreads();
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            st_stream(reinterpret_cast<uint32_t*>(sm.valptr[sm.dig[idx]]) + idx, sm.sorted[idx]);
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < K; ++j) {
+            const uint32_t idx = j * THREADS + tid;
+            if (idx < valid) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[sm.dig[idx]]) + idx, sm.sorted[idx]);
+        }
+    }
+}
+
+// =====================================================================================================
 // DigitBinningPass, variant 1 ("ring"): persistent CTAs, partition tiles staged by TMA bulk copies (cp.async.bulk,
 // SASS UBLKCP) into a two-deep shared-memory ring, with the wide kernel's ranking (two atomics per key), compact
 // reductions and windowed lookback.  While a CTA ranks and scatters tile p, the keys of its next tile are already
@@ -1185,7 +1387,10 @@ template <typename KeyT, bool PAIRS> struct WideGeom;
 #endif
 template <> struct WideGeom<uint32_t, false> { static constexpr int K = OSB_WIDE_K, WARPS = OSB_WIDE_WARPS, MINB = OSB_WIDE_MINB, LOOK = OSB_LOOK, STEP = OSB_STEP; };
 template <> struct WideGeom<uint32_t, true>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
-template <> struct WideGeom<uint64_t, false> { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
+#ifndef OSB_U64_K
+#define OSB_U64_K 16
+#endif
+template <> struct WideGeom<uint64_t, false> { static constexpr int K = OSB_U64_K, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
 
 template <typename KeyT, bool PAIRS, int RANK_MODE>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
@@ -1209,6 +1414,38 @@ static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t
         static_cast<KeyT*>(const_cast<void*>(in)), static_cast<KeyT*>(out), const_cast<uint32_t*>(in_val), out_val, n, gbase,
         agg16, incl64, ticket, pp, cfg.codec);
     return cudaGetLastError();
+}
+
+constexpr int kPairsK = 32, kPairsWarps = 16;
+
+template <int RANK_MODE>
+static cudaError_t launch_pairs_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
+                                        uint32_t shift, const unsigned long long* gbase, uint16_t* agg16, uint64_t* incl64,
+                                        uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg, cudaStream_t stream)
+{
+    using S = PairsSmem<kPairsWarps, kPairsK>;
+    const uint64_t tiles = (n + S::T - 1) / S::T;
+    PassParams pp;
+    pp.shift = shift;
+    pp.dbits = cfg.digit_bits;
+    pp.epoch = epoch;
+    pp.place = cfg.place;
+    pp.spin_cap = cfg.spin_cap;
+    pp.stall_every = cfg.debug_stall_every;
+    pp.plan = cfg.plan;
+    auto kern = digit_binning_pairs_kernel<kPairsK, kPairsWarps, RANK_MODE, OSB_LOOK, OSB_STEP>;
+    kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
+        static_cast<uint32_t*>(const_cast<void*>(in)), static_cast<uint32_t*>(out), const_cast<uint32_t*>(in_val), out_val, n,
+        gbase, agg16, incl64, ticket, pp, cfg.codec);
+    return cudaGetLastError();
+}
+
+template <int RANK_MODE>
+static cudaError_t set_pairs_attr()
+{
+    using S = PairsSmem<kPairsWarps, kPairsK>;
+    return cudaFuncSetAttribute(digit_binning_pairs_kernel<kPairsK, kPairsWarps, RANK_MODE, OSB_LOOK, OSB_STEP>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
 }
 
 template <typename KeyT, bool PAIRS, int RANK_MODE>
@@ -1255,7 +1492,7 @@ uint32_t binning_tile_keys(int key_bytes, bool pairs, const BinningConfig& cfg)
         return key_bytes == 8 ? RingGeom<uint64_t>::K * RingGeom<uint64_t>::WARPS * 32 : RingGeom<uint32_t>::K * RingGeom<uint32_t>::WARPS * 32;
     if (cfg.variant == kVariantWide) {
         if (key_bytes == 8) return WideGeom<uint64_t, false>::K * WideGeom<uint64_t, false>::WARPS * 32;
-        return pairs ? WideGeom<uint32_t, true>::K * WideGeom<uint32_t, true>::WARPS * 32
+        return pairs ? (OSB_PAIRS16K ? kPairsK * kPairsWarps * 32 : WideGeom<uint32_t, true>::K * WideGeom<uint32_t, true>::WARPS * 32)
                      : WideGeom<uint32_t, false>::K * WideGeom<uint32_t, false>::WARPS * 32;
     }
     if (key_bytes == 8) return TileGeom<uint64_t, false>::WARPS * 32 * TileGeom<uint64_t, false>::K;
@@ -1299,6 +1536,8 @@ cudaError_t configure_kernels()
     if ((e = set_wide_attr<uint32_t, true, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint64_t, false, kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_wide_attr<uint64_t, false, kRankBallot>()) != cudaSuccess) return e;
+    if ((e = set_pairs_attr<kRankAtomic>()) != cudaSuccess) return e;
+    if ((e = set_pairs_attr<kRankBallot>()) != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1320,6 +1559,9 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
                                                            ticket, epoch, cfg, stream)                                 \
             : launch_wide_variant<KEYT, PAIRS, kRankAtomic>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, \
                                                            ticket, epoch, cfg, stream))
+        if (key_bytes == 4 && pairs && OSB_PAIRS16K)
+            return ballot ? launch_pairs_variant<kRankBallot>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, ticket, epoch, cfg, stream)
+                          : launch_pairs_variant<kRankAtomic>(in, out, in_val, out_val, n, shift, gbase_place, agg16, desc, ticket, epoch, cfg, stream);
         if (key_bytes == 4) return pairs ? OSB_WIDE(uint32_t, true) : OSB_WIDE(uint32_t, false);
         if (key_bytes == 8 && !pairs) return OSB_WIDE(uint64_t, false);
 #undef OSB_WIDE

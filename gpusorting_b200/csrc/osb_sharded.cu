@@ -56,6 +56,7 @@ struct osb200_sharded_sorter {
     unsigned long long* d_out_base = nullptr;  // [256] virtual element indices (fused mode)
     unsigned long long* h_hist_all = nullptr;  // pinned
     unsigned long long* h_out_base = nullptr;  // pinned
+    unsigned long long* h_coarse_hist = nullptr;  // pinned
     uint32_t* d_flag = nullptr;                // 1-element all-reduce used as a stream-ordered cross-GPU barrier
     void* peer_recv[kMaxWorld] = {};           // IPC-mapped receive buffers of all ranks (own = recv_buf)
     bool fused = true;
@@ -140,6 +141,7 @@ int osb200_sharded_destroy(osb200_sharded_handle h)
     cudaFree(h->d_flag);
     cudaFreeHost(h->h_hist_all);
     cudaFreeHost(h->h_out_base);
+    cudaFreeHost(h->h_coarse_hist);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     if (h->comm) ncclCommDestroy(h->comm);
     delete h;
@@ -175,6 +177,7 @@ int osb200_sharded_create(osb200_sharded_handle* out, const void* unique_id_128_
     ok = ok && cudaMalloc(&s->d_flag, 64) == cudaSuccess;
     ok = ok && cudaMallocHost(&s->h_hist_all, static_cast<size_t>(world) * kRadix * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMallocHost(&s->h_out_base, kRadix * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&s->h_coarse_hist, kRadix * sizeof(unsigned long long)) == cudaSuccess;
     for (auto& e : s->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     if (!ok) { cudaGetLastError(); osb200_sharded_destroy(s); return OSB200_ERR_ALLOC; }
     cudaMemset(s->d_flag, 0, 64);
@@ -306,8 +309,9 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
         for (int b = 0; b < kRadix; ++b) h->h_out_base[b] = 0;
         const unsigned long long* my_hist = h->h_hist_all + static_cast<size_t>(h->rank) * kRadix;
         for (int d = 0; d < kRadix; ++d) h->h_out_base[d / per] += my_hist[d];
-        OSB_TRY(cudaMemcpyAsync(h->d_hist, h->h_out_base, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
-        OSB_TRY(cudaStreamSynchronize(q));  // h_out_base is reused below
+        // (staged through its own pinned buffer: no host sync needed before h_out_base is filled again below)
+        std::memcpy(h->h_coarse_hist, h->h_out_base, kRadix * sizeof(unsigned long long));
+        OSB_TRY(cudaMemcpyAsync(h->d_hist, h->h_coarse_hist, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
     } else {
         st = osb200_sharded_plan(reinterpret_cast<const uint64_t*>(h->h_hist_all), R, h->rank, dest, recv_count, recv_off);
         if (st != OSB200_OK) return st;
@@ -360,8 +364,11 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
     }
     OSB_TRY(cudaEventRecord(h->ev[2], q));
 
-    // 5. local OneSweep
-    st = osb200_sort_keys_u32(h->local, h->recv_buf, mine, q);
+    // 5. local OneSweep.  After a coarse exchange every key of this rank has the same top log2(R) bits: the local sort
+    //    runs on the bits below them only (its last digit is 8 - log2(R) bits wide: fewer bins, longer runs), and any
+    //    digit on which the received keys happen to agree is skipped on the device.
+    st = coarse ? osb200_sort_bits(h->local, h->recv_buf, nullptr, mine, 0, static_cast<int>(xshift), q)
+                : osb200_sort_keys_u32(h->local, h->recv_buf, mine, q);
     if (st != OSB200_OK) return st;
     OSB_TRY(cudaEventRecord(h->ev[3], q));
     *d_out = h->recv_buf;

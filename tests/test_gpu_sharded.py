@@ -72,3 +72,60 @@ def test_sharded_sort_matches_global_sort(fused, fine):
         assert p.exitcode == 0
     res = sorted(q.get(timeout=5) for _ in range(world))
     assert all(ok for _, ok in res)
+
+
+def _overflow_worker(rank, world, port, n, q):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gpusorting_b200 as g
+        from gpusorting_b200 import sharded
+        from tests import oraclelib
+
+        orc = oraclelib.load_oracle()
+        s = sharded.ShardedSorter(n, slack_percent=10)
+        # every rank holds only keys of ONE top byte: the whole input lands on a single rank, far beyond the 10 % slack
+        keys = (orc.init_random_u32(n, 0, 3 + rank) & np.uint32(0x00FFFFFF)) | np.uint32(0x42000000)
+        t = torch.from_numpy(keys.view(np.int32).copy()).cuda()
+        status = None
+        try:
+            s.sort_keys(t)
+        except g.OneSweepError as e:
+            status = e.status
+        torch.cuda.synchronize()
+        # the sorter is still usable afterwards: nobody is stuck in a collective
+        keys2 = orc.init_random_u32(n, 0, 50 + rank)
+        res = s.sort_keys(torch.from_numpy(keys2.view(np.int32).copy()).cuda())
+        torch.cuda.synchronize()
+        ok = status == -2 and res.numel() > 0 and bool((res[1:].to(torch.int64) & 0xFFFFFFFF >= res[:-1].to(torch.int64) & 0xFFFFFFFF).all())
+        s.close()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slack_overflow_is_reported_by_every_rank_together():
+    """the capacity check must make ALL ranks return OSB200_ERR_SIZE (status -2) before any collective of
+    the exchange, not only the overloaded rank (which would leave the others spinning in a barrier)."""
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_overflow_worker, args=(r, world, port, 1 << 18, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert all(ok for _, ok in res)
