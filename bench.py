@@ -323,7 +323,7 @@ def main():
             "clocks": result["clocks"],
             "verified": result["verified"],
         }
-        for k in ("extra_configs", "ref_cuda", "phases_ms"):
+        for k in ("extra_configs", "ref_cuda", "entropy_sweep", "phases_ms"):
             if k in result:
                 line[k] = result[k]
         if world == 1 and not args.no_cpu_baseline:
@@ -428,6 +428,32 @@ def extra_config_u64(g, n, peak, steps=5, warmup=3):
             "roofline": {"bound": "hbm", "kernel": "digit_binning_wide_kernel<u64>", "achieved": round(ach, 1), "peak": peak,
                          "unit": "GB/s", "frac": round(ach / peak, 4), "algorithmic_bytes_per_launch": 16 * n, "launch_ms": round(pass_ms, 4)},
             "kernel_ms": {"global_histogram": round(prof[0], 4), "digit_binning_pass_mean": round(pass_ms, 4)}, "verified": bool(ok)}
+
+
+def entropy_sweep(g, n, steps=3, warmup=2):
+    """The reference's entropy benchmark (Thearling-Smith presets, UtilityKernels.cuh:42-52,70-81; chart README.md:27,
+    protocol GPUSortingD3D12/Tests.h:383-393): and_count 0..4 ANDs 1..5 uniform draws (32 -> ~1 bit of entropy per key
+    bit... 1.0, 0.811, 0.544, 0.337, 0.201 bits per bit), plus the degenerate cases that exercise pass skipping."""
+    import torch
+
+    src = torch.empty(n, dtype=torch.int32, device="cuda")
+    work = torch.empty_like(src)
+    s = g.OneSweepSorter(n, 4, 0)
+    stream = torch.cuda.current_stream()
+    out = []
+    cases = [(f"entropy_preset_{a + 1}", a, None) for a in range(5)] + [("low_16_bits_only", 0, 0xFFFF), ("all_equal", 0, 0)]
+    for name, andc, mask in cases:
+        g.init_random(src, andc, SEED)
+        if mask is not None:
+            src &= mask
+        ms = _time_sorts(steps, warmup, lambda: work.copy_(src), lambda: s.sort_keys(work), stream)
+        ok = s.validate(work) == 0
+        out.append({"input": name, "value": round(n / (ms / 1e3) / 1e9, 2), "unit": "Gkeys/s", "ms_per_sort": round(ms, 4),
+                    "executed_passes": s.info("last_executed_passes"), "sorted": bool(ok)})
+    s.close()
+    del src, work
+    torch.cuda.empty_cache()
+    return out
 
 
 def ref_cuda_leg(n):
@@ -535,6 +561,7 @@ def bench_single(args, g, n, device_index):
         peak, _ = measured_peak_gbs()
         out["extra_configs"] = [extra_config_pairs(g, n, peak), extra_config_u64(g, n, peak)]
         out["ref_cuda"] = ref_cuda_leg(n)
+        out["entropy_sweep"] = entropy_sweep(g, n)
     return out
 
 

@@ -1,11 +1,15 @@
 // main_cli.cpp -- the reference's test/benchmark driver (GPUSortingCUDA/GPUSortingCUDA.cu:16-57) for the B200 path:
 // TestAllKeysOnly / TestAllPairs sweeps, then BatchTiming at 2^28 with 100 iterations, seed 10 -- through the C-ABI.
-// Build: make -C gpusorting_b200/csrc cli     Run (GPU box): gpusorting_b200/lib/onesweep_b200_cli [log2n] [iters]
+// Build: make -C gpusorting_b200/csrc cli (also done by __graft_entry__.build()).
+// Run (GPU box): gpusorting_b200/lib/onesweep_b200_cli [log2n=28] [iters=100] [sweep_step=1] [max_log2=28]
+// (the reference's main is the defaults; tests/test_gpu_parity.py::test_cli_runs_the_reference_protocol uses a coarse sweep)
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "../../include/OneSweepB200.hpp"
+
+static uint32_t g_sweep_step = 1, g_max_log2 = 28;
 
 static bool test_sweep(bool pairs, uint32_t max_n)
 {
@@ -21,8 +25,8 @@ static bool test_sweep(bool pairs, uint32_t max_n)
         passed += ok; ++total;
         if (!ok) printf("\n Test failed at size %u \n", n);
     };
-    for (uint32_t n = 7680; n <= 15360; ++n) { one(n, n); if (!(n & 255)) { printf("."); fflush(stdout); } }
-    for (uint32_t e = 26; e <= 28 && (1u << e) <= max_n; ++e) one(1u << e, e);
+    for (uint32_t n = 7680; n <= 15360; n += g_sweep_step) { one(n, n); if (!(n & 255)) { printf("."); fflush(stdout); } }
+    for (uint32_t e = g_max_log2 >= 28 ? 26 : g_max_log2; e <= g_max_log2 && (1u << e) <= max_n; ++e) one(1u << e, e);
     printf("\n%u/%u %s\n\n", passed, total, passed == total ? "All tests passed." : "Test failed.");
     cudaFree(keys); cudaFree(vals);
     return passed == total;
@@ -53,12 +57,15 @@ static void batch_timing(bool pairs, uint32_t size, uint32_t batch, uint32_t see
 int main(int argc, char** argv)
 {
     const uint32_t log2n = argc > 1 ? atoi(argv[1]) : 28, iters = argc > 2 ? atoi(argv[2]) : 100;
+    if (argc > 3) g_sweep_step = atoi(argv[3]) > 0 ? atoi(argv[3]) : 1;
+    if (argc > 4) g_max_log2 = atoi(argv[4]);
+    const uint32_t cap = 1u << (g_max_log2 > log2n ? g_max_log2 : log2n);
     try {
         printf("Beginning B200 OneSweep keys validation test: \n");
-        bool ok = test_sweep(false, 1u << 28);
+        bool ok = test_sweep(false, cap);
         batch_timing(false, 1u << log2n, iters, 10);
         printf("Beginning B200 OneSweep pairs validation test: \n");
-        ok = test_sweep(true, 1u << 28) && ok;
+        ok = test_sweep(true, cap) && ok;
         batch_timing(true, 1u << log2n, iters, 10);
         return ok ? 0 : 1;
     } catch (const std::exception& e) {

@@ -33,6 +33,17 @@ class OneSweepSorterB200 {
     {
         check(osb200_sort_pairs_u32(h_, d_keys, d_values, n, stream), "osb200_sort_pairs_u32");
     }
+    // stable sort on the key bits [begin_bit, end_bit) only; d_values may be null
+    void SortBits(void* d_keys, uint32_t* d_values, uint64_t n, int begin_bit, int end_bit, void* stream = nullptr)
+    {
+        check(osb200_sort_bits(h_, d_keys, d_values, n, begin_bit, end_bit, stream), "osb200_sort_bits");
+    }
+    // signed / float keys and descending order (osb200_key_type)
+    void SortKeysTyped(void* d_keys, uint64_t n, int key_type, bool descending, void* stream = nullptr)
+    {
+        check(osb200_sort_keys_typed(h_, d_keys, n, key_type, descending ? 1 : 0, stream), "osb200_sort_keys_typed");
+    }
+    void SetOption(const char* key, int64_t value) { check(osb200_set_option(h_, key, value), "osb200_set_option"); }
     uint64_t Validate(const void* d_keys, uint64_t n, void* stream = nullptr)
     {
         uint64_t e = 0;

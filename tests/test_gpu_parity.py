@@ -332,3 +332,16 @@ def test_dispatcher_mirror_runs_reference_tests(g):
     assert passed == total
     with pytest.raises(ValueError):
         d.BatchTimingPairs(1 << 20, 1, 10)
+
+
+def test_cli_runs_the_reference_protocol():
+    """The C++ driver that restates the reference's main (GPUSortingCUDA.cu:16-57: TestAll sweeps + BatchTiming) on top
+    of include/OneSweepB200.hpp: coarse sweep, 2^20 timing."""
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpusorting_b200", "lib", "onesweep_b200_cli")
+    if not os.path.exists(exe):
+        pytest.skip("onesweep_b200_cli not built (make -C gpusorting_b200/csrc cli)")
+    r = subprocess.run([exe, "20", "3", "257", "22"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("All tests passed.") == 2 and r.stdout.count("Estimated speed") == 2
