@@ -89,6 +89,8 @@ struct osb200_sorter {
 namespace {
 
 uint64_t tiles_for(uint64_t n, uint32_t tile_keys) { return (n + tile_keys - 1) / tile_keys; }
+// the compact reductions are stored in blocks of 8 tiles ([tile/8][digit][tile%8], see osb_kernels.cu agg_index)
+uint64_t agg_tiles_for(uint64_t n, uint32_t tile_keys) { return (tiles_for(n, tile_keys) + 7) / 8 * 8; }
 
 uint32_t smallest_tile(int key_bytes, bool pairs)
 {
@@ -140,7 +142,7 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
 
     OSB_TRY(cudaMemsetAsync(s->control, 0, ControlLayout::zeroed_bytes, stream));
     const bool compact = s->cfg.variant != osb::kVariantTilePerCta;  // every other variant uses the compact reductions
-    const uint64_t agg_stride = tiles_for(n, osb::binning_tile_keys(s->key_bytes, d_vals != nullptr, s->cfg)) * osb::kRadix;
+    const uint64_t agg_stride = agg_tiles_for(n, osb::binning_tile_keys(s->key_bytes, d_vals != nullptr, s->cfg)) * osb::kRadix;
     // reductions carry no epoch (16-bit words): they are cleared per sort, 512 B per tile and place (128 MiB at n = 2^30)
     if (compact) OSB_TRY(cudaMemsetAsync(s->agg16, 0, agg_stride * places * sizeof(uint16_t), stream));
     int ne = 0;
@@ -251,7 +253,7 @@ int osb_internal_binning_pass(osb200_handle h, const void* d_in, void* d_out, ui
         base = h->gbase();
     }
     if (h->cfg.variant != osb::kVariantTilePerCta) {
-        const uint64_t tiles = tiles_for(n, osb::binning_tile_keys(h->key_bytes, false, h->cfg));
+        const uint64_t tiles = agg_tiles_for(n, osb::binning_tile_keys(h->key_bytes, false, h->cfg));
         OSB_TRY(cudaMemsetAsync(h->agg16, 0, tiles * osb::kRadix * sizeof(uint16_t), stream));
     }
     uint32_t epoch = 0;
@@ -289,8 +291,8 @@ uint64_t osb200_workspace_bytes(uint64_t max_n, int key_bytes, int value_bytes)
 {
     if ((key_bytes != 4 && key_bytes != 8) || (value_bytes != 0 && value_bytes != 4)) return 0;
     const uint64_t tiles = tiles_for(max_n ? max_n : 1, smallest_tile(key_bytes, value_bytes != 0));
-    return max_n * key_bytes + max_n * value_bytes + tiles * osb::kRadix * (sizeof(uint64_t) + sizeof(uint16_t) * key_bytes) +
-           ControlLayout::total;
+    return max_n * key_bytes + max_n * value_bytes + tiles * osb::kRadix * sizeof(uint64_t) +
+           (tiles + 8) * osb::kRadix * sizeof(uint16_t) * key_bytes + ControlLayout::total;
 }
 
 int osb200_create(osb200_handle* out, uint64_t max_n, int key_bytes, int value_bytes)
@@ -325,7 +327,7 @@ int osb200_create(osb200_handle* out, uint64_t max_n, int key_bytes, int value_b
     if (ok && value_bytes) ok = cudaMalloc(&s->alt_vals, max_n * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&s->control, ControlLayout::total) == cudaSuccess;
     ok = ok && cudaMalloc(&s->desc, s->desc_tiles * osb::kRadix * sizeof(uint64_t)) == cudaSuccess;
-    ok = ok && cudaMalloc(&s->agg16, s->desc_tiles * osb::kRadix * sizeof(uint16_t) * key_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->agg16, (s->desc_tiles + 8) * osb::kRadix * sizeof(uint16_t) * key_bytes) == cudaSuccess;
     if (!ok) { cudaGetLastError(); osb200_destroy(s); return OSB200_ERR_ALLOC; }
     e = cudaMemset(s->desc, 0, s->desc_tiles * osb::kRadix * sizeof(uint64_t));  // epoch 0 == never valid
     if (e == cudaSuccess) e = cudaMemset(s->control, 0, ControlLayout::total);
@@ -475,7 +477,7 @@ int osb200_digit_binning_pass(osb200_handle h, const void* d_in, void* d_out, co
     OSB_TRY(cudaMemsetAsync(h->tickets(), 0, ControlLayout::ticket_bytes, q));
     OSB_TRY(osb::launch_scan(h->ghist(), h->gbase(), 1, q));
     if (h->cfg.variant != osb::kVariantTilePerCta)
-        OSB_TRY(cudaMemsetAsync(h->agg16, 0, h->desc_tiles * osb::kRadix * sizeof(uint16_t), q));
+        OSB_TRY(cudaMemsetAsync(h->agg16, 0, (h->desc_tiles + 8) * osb::kRadix * sizeof(uint16_t), q));
     uint32_t epoch = 0;
     st = next_epoch(h, q, &epoch);
     if (st != OSB200_OK) return st;

@@ -580,6 +580,51 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 // IS the key's slot in the digit-sorted tile (lane-ordered, see top of file).  No per-key offsets are kept in
 // registers, so 32 keys per thread fit in a 64-register budget (2 x 512 threads per SM).
 // =====================================================================================================
+// OSB_EXP: compile-time experiments for tools/sweep.sh, OFF (0) in the product build (measured in round 2,
+// profiles/r02_experiments.md):
+//   bit 2 (4): the chained-scan lookback runs BEFORE the rank phase (digit warps look back while the other warps rank)
+//   bit 3 (8): full tiles are staged by ONE TMA bulk copy (cp.async.bulk + mbarrier) into the sorted-tile buffer, then LDS
+//   bit 5 (32): per-phase clock probe (tools/phase_probe.py)
+#ifndef OSB_EXP
+#define OSB_EXP 0
+#endif
+// OSB_TICKET 1: tiles are handed out by an atomic ticket (the reference's scheme, OneSweep.cu:181-184) instead of blockIdx.x.
+// Default 0 (measured -2.3% per pass, profiles/r02_experiments.md): the ticket's L2 round trip sat in front of every tile's
+// loads.  Without it forward progress rests on the lookback's spin cap + fallback re-reduction, not on the dispatch order.
+#ifndef OSB_TICKET
+#define OSB_TICKET 0
+#endif
+#if (OSB_EXP & 8) && !OSB_TICKET
+#error "the TMA tile-load experiment (OSB_EXP bit 3) is written for the ticket path: build with -DOSB_TICKET=1"
+#endif
+// OSB_ABL: timing-only ablations for tools/sweep.sh (the output is WRONG; never set in the product build):
+//   1 no lookback (prior = tile * const)   2 no global stores in the scatter   4 no count atomics   8 no rank atomics / transposing stores
+//   16 no scatter loop at all (use with 2)
+#ifndef OSB_ABL
+#define OSB_ABL 0
+#endif
+
+#if OSB_EXP & (32 | 128)
+// (development) per-phase wall clocks of the wide kernel, summed over CTAs by thread 0: [0]=ticket+clear, [1]=load, [2]=count,
+// [3]=reduce/scan/bases, [4]=rank, [5]=lookback, [6]=scatter, [7]=CTAs
+__device__ unsigned long long g_phase[16];  // [8]=barrier after lookback, [9]=lookback windows (digit 0), [10]=stalled polls
+#if OSB_EXP & 32
+#define OSB_PHASE(i) do { if (tid == 0) { const long long t_now = clock64(); atomicAdd(&g_phase[i], static_cast<unsigned long long>(t_now - t_prev)); t_prev = t_now; } } while (0)
+#else
+#define OSB_PHASE(i) do {} while (0)
+#endif
+}  // namespace osb
+extern "C" __attribute__((visibility("default"))) int osb200_debug_phases(unsigned long long* out8 /*[16]*/, int reset)
+{
+    if (out8) cudaMemcpyFromSymbol(out8, osb::g_phase, sizeof(osb::g_phase));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(osb::g_phase, z, sizeof(z)); }
+    return 0;
+}
+namespace osb {
+#else
+#define OSB_PHASE(i) do {} while (0)
+#endif
+
 constexpr uint32_t kAggReady = 0x8000u;   // agg16 word: bit 15 = reduction published, bits 0..14 = count
 
 __device__ __forceinline__ uint32_t ld_relaxed_gpu_u16(const uint16_t* p)
@@ -624,60 +669,98 @@ __device__ __noinline__ uint32_t rereduce_tile(const KeyT* p, uint32_t tile_keys
     return c;
 }
 
-// Decoupled lookback over the compact reductions.  Examines up to LOOK predecessors per round trip, with an
-// inclusive-prefix probe every STEP tiles.  Returns the number of keys with digit d in all predecessor tiles
-// (relative to the start of the array: the global digit base is added by the caller, so descriptor values stay
-// below n even when the bases are peer addresses in the sharded exchange pass).  A predecessor whose reduction is
-// still missing after spin_cap polls is re-reduced by this thread (rereduce_tile): the spin is bounded.
-template <int LOOK, int STEP, typename KeyT>
+// Layout of the compact reductions: blocks of 8 consecutive tiles, [tile / 8][digit][tile % 8] 16-bit words, so that ONE
+// 16-byte load returns a digit's reductions of 8 consecutive tiles.  (Round 1 stored them [tile][digit] and fetched them
+// with eight 2-byte loads per window: the phase probe of round 2 -- profiles/r02_phase_probe.md -- showed 3.8 windows of
+// ~2,400 clocks each per tile, a third of a CTA's lifetime.)
+__device__ __forceinline__ uint64_t agg_index(uint64_t tile, uint32_t d) { return ((tile >> 3) * kRadix + d) * 8 + (tile & 7); }
+
+__device__ __forceinline__ uint4 ld_relaxed_gpu_v4(const void* p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// 16-bit element t (0..7) of a block vector
+__device__ __forceinline__ uint32_t agg_elem(const uint4& v, int t)
+{
+    const uint32_t w = t < 2 ? v.x : t < 4 ? v.y : t < 6 ? v.z : v.w;
+    return (t & 1) ? (w >> 16) : (w & 0xffffu);
+}
+
+// Decoupled lookback over the compact reductions.  One round trip fetches NBLK blocks of 8 tiles (the nearest one partial:
+// the predecessors inside this tile's own block) plus, per block, the inclusive prefix of the tile just before it.  Returns
+// the number of keys with digit d in all predecessor tiles (relative to the start of the array: the global digit base is
+// added by the caller, so descriptor values stay below n even when the bases are peer addresses in the sharded exchange
+// pass).  A predecessor whose reduction is still missing after spin_cap polls is re-reduced by this thread
+// (rereduce_tile): the spin is bounded.
+template <int NBLK, typename KeyT>
 __device__ __forceinline__ unsigned long long
 lookback_wide(uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d, uint32_t epoch, uint32_t spin_cap,
               const TileRereduce<KeyT>& rr)
 {
-    static_assert(LOOK % STEP == 0, "probe spacing must divide the window");
     unsigned long long sum = 0;                       // reductions of tiles (cur, tile-1] already added
     int64_t cur = static_cast<int64_t>(tile) - 1;     // nearest predecessor not yet accounted for
     uint32_t polls = 0;                               // consecutive unsuccessful polls of tile `cur`
     while (true) {
         if (cur < 0) return sum;
-        uint32_t a[LOOK];
-        uint64_t c[LOOK / STEP];
+#if OSB_EXP & (32 | 128)
+        if (d == 0) atomicAdd(&g_phase[9], 1ull);
+#endif
+        const int64_t b0 = cur >> 3;
+        uint4 v[NBLK];
+        uint64_t c[NBLK];
 #pragma unroll
-        for (int i = 0; i < LOOK; ++i) {
-            const int64_t t = cur - i;
-            a[i] = t >= 0 ? ld_relaxed_gpu_u16(agg16 + t * kRadix + d) : kAggReady;
-        }
-#pragma unroll
-        for (int j = 0; j < LOOK / STEP; ++j) {
-            const int64_t t = cur - (j * STEP + STEP - 1);
-            c[j] = t >= 0 ? ld_relaxed_gpu_u64(incl64 + t * kRadix + d) : 0ull;
+        for (int k = 0; k < NBLK; ++k) {
+            const int64_t b = b0 - k;
+#ifdef OSB_DBG_SCALAR_AGG
+            if (b >= 0) {
+                const uint16_t* q = agg16 + (static_cast<uint64_t>(b) * kRadix + d) * 8;
+                v[k].x = ld_relaxed_gpu_u16(q) | (ld_relaxed_gpu_u16(q + 1) << 16);
+                v[k].y = ld_relaxed_gpu_u16(q + 2) | (ld_relaxed_gpu_u16(q + 3) << 16);
+                v[k].z = ld_relaxed_gpu_u16(q + 4) | (ld_relaxed_gpu_u16(q + 5) << 16);
+                v[k].w = ld_relaxed_gpu_u16(q + 6) | (ld_relaxed_gpu_u16(q + 7) << 16);
+            } else v[k] = make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+#else
+            v[k] = b >= 0 ? ld_relaxed_gpu_v4(agg16 + (static_cast<uint64_t>(b) * kRadix + d) * 8)
+                          : make_uint4(0x80008000u, 0x80008000u, 0x80008000u, 0x80008000u);
+#endif
+            c[k] = b > 0 ? ld_relaxed_gpu_u64(incl64 + (static_cast<uint64_t>(b) * 8 - 1) * kRadix + d) : 0ull;
         }
         unsigned long long run = sum;
-        int64_t next = cur - LOOK;  // where to continue if the whole window was reductions only
+        int64_t next = (b0 - NBLK + 1) * 8 - 1;  // where to continue if the whole window was reductions only
         bool stalled = false;
+        const int hi0 = static_cast<int>(cur & 7);
 #pragma unroll
-        for (int i = 0; i < LOOK; ++i) {
-            const int64_t t = cur - i;
-            if (t < 0) return run;
-            if ((i % STEP) == STEP - 1) {
-                const uint64_t v = c[i / STEP];
-                if (desc_epoch(v) == epoch && (v & kFlagMask) == kFlagInclusive) return run + desc_value(v);
+        for (int k = 0; k < NBLK; ++k) {
+            const int64_t b = b0 - k;
+            if (b < 0) return run;
+#pragma unroll
+            for (int t = 7; t >= 0; --t) {
+                if (k == 0 && t > hi0) continue;
+                const uint32_t a = agg_elem(v[k], t);
+                if (!(a & kAggReady)) { next = b * 8 + t; stalled = true; break; }
+                run += a & 0x7fffu;
             }
-            if (!(a[i] & kAggReady)) { next = t; stalled = true; break; }
-            run += a[i] & 0x7fffu;
+            if (stalled) break;
+            if (b == 0) return run;  // tile 0 has no predecessors
+            if (desc_epoch(c[k]) == epoch && (c[k] & kFlagMask) == kFlagInclusive) return run + desc_value(c[k]);
         }
         sum = run;
         if (stalled) {
             polls = next == cur ? polls + 1 : 1;
             if (polls > spin_cap) {
                 // maybe the stalled tile has finished altogether meanwhile: its inclusive prefix settles everything
-                const uint64_t v = ld_relaxed_gpu_u64(incl64 + next * kRadix + d);
-                if (desc_epoch(v) == epoch && (v & kFlagMask) == kFlagInclusive) return sum + desc_value(v);
+                const uint64_t w = ld_relaxed_gpu_u64(incl64 + next * kRadix + d);
+                if (desc_epoch(w) == epoch && (w & kFlagMask) == kFlagInclusive) return sum + desc_value(w);
                 sum += rereduce_tile<KeyT>(rr.in + static_cast<uint64_t>(next) * rr.tile_keys, rr.tile_keys, rr.shift, rr.mask,
-                                           rr.encode ? 1u : 0u, rr.ca, rr.cb, rr.cd, agg16 + next * kRadix + d, d);
+                                           rr.encode ? 1u : 0u, rr.ca, rr.cb, rr.cd, agg16 + agg_index(next, d), d);
                 --next;
                 polls = 0;
             } else {
+#if OSB_EXP & (32 | 128)
+                if (d == 0) atomicAdd(&g_phase[10], 1ull);
+#endif
                 __nanosleep(40);
             }
         } else {
@@ -686,21 +769,6 @@ lookback_wide(uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d
         cur = next;
     }
 }
-
-// OSB_EXP: compile-time experiments for tools/sweep.sh, OFF (0) in the product build (measured in round 2,
-// profiles/r02_experiments.md):
-//   bit 0 (1): 32-bit element offsets per digit instead of 64-bit byte pointers in the scatter (valid for n <= 2^32, out != 0)
-//   bit 2 (4): the chained-scan lookback runs BEFORE the rank phase (digit warps look back while the other warps rank)
-//   bit 3 (8): full tiles are staged by ONE TMA bulk copy (cp.async.bulk + mbarrier) into the sorted-tile buffer, then LDS
-#ifndef OSB_EXP
-#define OSB_EXP 0
-#endif
-// OSB_ABL: timing-only ablations for tools/sweep.sh (the output is WRONG; never set in the product build):
-//   1 no lookback (prior = tile * const)   2 no global stores in the scatter   4 no count atomics   8 no rank atomics / transposing stores
-//   16 no scatter loop at all (use with 2)
-#ifndef OSB_ABL
-#define OSB_ABL 0
-#endif
 
 // Per-launch parameters of one DigitBinningPass.
 struct PassParams {
@@ -723,9 +791,6 @@ struct WideSmem {
     unsigned long long keyptr[kRadix];               // per digit: byte address of out[first key of the digit - tile slot]
     unsigned long long valptr[PAIRS ? kRadix : 1];
     uint32_t run[32];                                // few-bins passes: first slot (low 16 bits) | live length (high 16)
-#if OSB_EXP & 1
-    uint32_t off32[kRadix];                          // element index of tile slot 0 "as if" of this digit, mod 2^32
-#endif
     uint32_t wtot[kRadix / 32];
     uint32_t tile;                                   // this CTA's tile, 0xffffffff = the plan skips this pass
     uint32_t plan_bits;                              // bit 0: source is the alt buffer; bits 1-2: codec flags of this pass
@@ -750,11 +815,36 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     uint32_t* wh = sm.hist + warp * kRadix;
     const uint32_t shift = pp.shift, epoch = pp.epoch;
     const uint32_t dmask = (1u << pp.dbits) - 1u;
+#if OSB_EXP & 32
+    long long t_prev = clock64();
+#endif
 
     {
         uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
         for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
     }
+#if !OSB_TICKET
+    // tile id = blockIdx.x: no ticket round trip before the loads.  Forward progress no longer rests on the dispatch order (the
+    // hardware starts CTAs in blockIdx order in practice): a predecessor that is not running is re-reduced by its successors
+    // after spin_cap polls (rereduce_tile), so the chained scan cannot hang.  Every thread reads the 16-byte plan itself (L1 hit
+    // for all but the first CTA of an SM).
+    uint32_t my_bits = (codec.flags & (kCodecEncodeOnLoad | kCodecDecodeOnStore)) << 1;
+    bool my_skip = false;
+    if (pp.plan != nullptr) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(pp.plan));
+        SortPlan pl; pl.skip_mask = raw.x; pl.executed = raw.y; pl.first_exec = raw.z; pl.last_exec = raw.w;
+        my_skip = (pl.skip_mask >> pp.place) & 1u;
+        my_bits = plan_src_is_alt(pl, pp.place) ? 1u : 0u;
+        if (codec.flags & kCodecFromPlan)
+            my_bits |= (pp.place == pl.first_exec ? kCodecEncodeOnLoad << 1 : 0u) | (pp.place == pl.last_exec ? kCodecDecodeOnStore << 1 : 0u);
+    }
+    if (my_skip) return;
+    if (tid == 0) {
+        sm.plan_bits = my_bits;
+        sm.tile = blockIdx.x;
+    }
+    const uint32_t tile = blockIdx.x;
+#else
     if (tid == 0) {
         // The device plan (if any) decides whether this pass runs at all, which buffer it reads, and -- typed keys --
         // whether it is the pass that encodes / decodes.  Without a plan the launch arguments are taken as they are.
@@ -786,18 +876,24 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     __syncthreads();
     const uint32_t tile = sm.tile;
     if (tile == 0xffffffffu) return;  // all keys share this digit: nothing to move (the plan accounts for the parity)
+#endif
     // plan_bits (direction, codec flags) is re-read from shared memory where it is needed instead of being carried in
     // registers across the phases: the 64-register budget of this kernel is spent on the 32 keys and their counter addresses
     const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
     const bool full = tile_base + T <= n;
     const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
+    OSB_PHASE(0);
 
     // ---- load (warp-striped: every warp instruction reads one contiguous 128 B / 256 B row) ------------
     KeyT key[K];
     uint32_t val[PAIRS ? K : 1];
     const uint32_t warp_off = warp * (32 * K) + lane;
     {
+#if !OSB_TICKET
+    const bool swap = my_bits & 1u;
+#else
     const bool swap = sm.plan_bits & 1u;
+#endif
     const KeyT* __restrict__ in = swap ? buf1 : buf0;
     const uint32_t* __restrict__ in_val = swap ? val1 : val0;
     if (full) {
@@ -826,6 +922,9 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     // typed keys: the first executed pass of a sort turns the caller's keys into order-equivalent unsigned keys.  The
     // padding of the ragged last tile is encoded too and stays the largest key only if it was loaded as the pre-image of
     // all-ones, so it is simply re-set after encoding.
+#if !OSB_TICKET
+    __syncthreads();  // histograms cleared, plan_bits visible (the loads above are already in flight)
+#endif
     if ((sm.plan_bits >> 1) & kCodecEncodeOnLoad) {
         const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
 #pragma unroll
@@ -835,12 +934,18 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
         }
     }
 
+#if OSB_EXP & 32
+#pragma unroll
+    for (int i = 0; i < K; ++i) asm volatile("" ::"l"(static_cast<unsigned long long>(key[i])));  // all loads have landed
+    OSB_PHASE(1);
+#endif
     // ---- phase 1: count digits per warp (order-free, non-returning atomics) ---------------------------
 #if !(OSB_ABL & 4)
 #pragma unroll
     for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift, dmask)], 1u);
 #endif
     __syncthreads();
+    OSB_PHASE(2);
 
     // ---- per digit: tile reduction -> publish; scan over digits; per-warp slot bases --------------------
     uint32_t tile_count = 0, tile_excl = 0;
@@ -849,7 +954,7 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
         for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
         // (test hook: a "stalled" tile never publishes its reduction; its successors must re-reduce it themselves)
         if (pp.stall_every == 0 || (tile % pp.stall_every) != pp.stall_every - 1)
-            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+            st_relaxed_gpu_u16(agg16 + agg_index(tile, tid), kAggReady | tile_count);
     }
     tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
     if (tid < kRadix) {
@@ -858,6 +963,7 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
         for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
     }
     __syncthreads();
+    OSB_PHASE(3);
 
     // ---- chained scan with decoupled lookback (one thread per digit) -------------------------------------
     auto chained_scan = [&]() {
@@ -869,7 +975,7 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
             rr.in = (sm.plan_bits & 1u) ? buf1 : buf0; rr.tile_keys = T; rr.shift = shift; rr.mask = dmask;
             rr.encode = (sm.plan_bits >> 1) & kCodecEncodeOnLoad;
             rr.ca = static_cast<KeyT>(codec.a); rr.cb = static_cast<KeyT>(codec.b); rr.cd = static_cast<KeyT>(codec.d);
-            const unsigned long long prior = lookback_wide<LOOK, STEP, KeyT>(agg16, incl64, tile, tid, epoch, pp.spin_cap, rr);
+            const unsigned long long prior = lookback_wide<LOOK / 8, KeyT>(agg16, incl64, tile, tid, epoch, pp.spin_cap, rr);
 #endif
             const bool swap = sm.plan_bits & 1u;
             KeyT* out = swap ? buf0 : buf1;
@@ -885,9 +991,6 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
                 const uint32_t live = tile_count - ((tid == pad_digit && !full) ? (T - valid) : 0u);
                 sm.run[tid] = tile_excl | (live << 16);
             }
-#if OSB_EXP & 1
-            sm.off32[tid] = static_cast<uint32_t>(first);
-#endif
         }
     };
 #if OSB_EXP & 4
@@ -909,10 +1012,13 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     }
 #endif
 
+    OSB_PHASE(4);
 #if !(OSB_EXP & 4)
     chained_scan();
 #endif
+    OSB_PHASE(5);
     __syncthreads();
+    OSB_PHASE(8);
 
     // ---- scatter -----------------------------------------------------------------------------------------
     // Few bins (a digit of <= 5 bits: the sharded exchange on log2(R) bits): runs are thousands of keys long, so
@@ -941,16 +1047,6 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
                 }
             }
         }
-#if OSB_EXP & 1
-    } else if (full && !dec && !PAIRS && ((sm.plan_bits & 1u) ? buf0 : buf1) != nullptr) {
-        KeyT* out = (sm.plan_bits & 1u) ? buf0 : buf1;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const uint32_t idx = j * THREADS + tid;
-            const KeyT k = sm.sorted[idx];
-            st_stream(out + static_cast<uint32_t>(sm.off32[digit_of(k, shift, dmask)] + idx), k);
-        }
-#endif
 #if OSB_ABL & 16
     } else if (full && !dec) {
 #endif
@@ -982,6 +1078,10 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
             }
         }
     }
+    OSB_PHASE(6);
+#if OSB_EXP & 32
+    if (tid == 0) atomicAdd(&g_phase[7], 1ull);
+#endif
 }
 
 // =====================================================================================================
@@ -1036,6 +1136,20 @@ digit_binning_pairs_kernel(uint32_t* buf0, uint32_t* buf1, uint32_t* val0, uint3
         uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
         for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
     }
+#if !OSB_TICKET
+    // tile id = blockIdx.x, every thread reads the plan itself (see digit_binning_wide_kernel)
+    uint32_t my_bits = (codec.flags & (kCodecEncodeOnLoad | kCodecDecodeOnStore)) << 1;
+    if (pp.plan != nullptr) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(pp.plan));
+        SortPlan pl; pl.skip_mask = raw.x; pl.executed = raw.y; pl.first_exec = raw.z; pl.last_exec = raw.w;
+        if ((pl.skip_mask >> pp.place) & 1u) return;
+        my_bits = plan_src_is_alt(pl, pp.place) ? 1u : 0u;
+        if (codec.flags & kCodecFromPlan)
+            my_bits |= (pp.place == pl.first_exec ? kCodecEncodeOnLoad << 1 : 0u) | (pp.place == pl.last_exec ? kCodecDecodeOnStore << 1 : 0u);
+    }
+    if (tid == 0) { sm.plan_bits = my_bits; sm.tile = blockIdx.x; }
+    const uint32_t tile = blockIdx.x;
+#else
     if (tid == 0) {
         const uint32_t drawn = atomicAdd(ticket, 1u);
         uint32_t bits = (codec.flags & (kCodecEncodeOnLoad | kCodecDecodeOnStore)) << 1;
@@ -1053,6 +1167,7 @@ digit_binning_pairs_kernel(uint32_t* buf0, uint32_t* buf1, uint32_t* val0, uint3
     __syncthreads();
     const uint32_t tile = sm.tile;
     if (tile == 0xffffffffu) return;
+#endif
     const uint64_t tile_base = static_cast<uint64_t>(tile) * T;
     const bool full = tile_base + T <= n;
     const uint32_t valid = full ? T : static_cast<uint32_t>(n - tile_base);
@@ -1061,7 +1176,11 @@ digit_binning_pairs_kernel(uint32_t* buf0, uint32_t* buf1, uint32_t* val0, uint3
     // ---- keys ---------------------------------------------------------------------------------------------
     uint32_t key[K];  // later: the payloads
     {
+#if !OSB_TICKET
+        const KeyT* __restrict__ in = (my_bits & 1u) ? buf1 : buf0;
+#else
         const KeyT* __restrict__ in = (sm.plan_bits & 1u) ? buf1 : buf0;
+#endif
         if (full) {
 #pragma unroll
             for (int i = 0; i < K; ++i) key[i] = ld_stream(in + tile_base + warp_off + i * 32);
@@ -1073,6 +1192,9 @@ digit_binning_pairs_kernel(uint32_t* buf0, uint32_t* buf1, uint32_t* val0, uint3
             }
         }
     }
+#if !OSB_TICKET
+    __syncthreads();  // histograms cleared, plan_bits visible (the loads above are already in flight)
+#endif
     if ((sm.plan_bits >> 1) & kCodecEncodeOnLoad) {
         const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
 #pragma unroll
@@ -1090,7 +1212,7 @@ digit_binning_pairs_kernel(uint32_t* buf0, uint32_t* buf1, uint32_t* val0, uint3
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
         if (pp.stall_every == 0 || (tile % pp.stall_every) != pp.stall_every - 1)
-            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+            st_relaxed_gpu_u16(agg16 + agg_index(tile, tid), kAggReady | tile_count);
     }
     tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
     if (tid < kRadix) {
@@ -1100,20 +1222,6 @@ digit_binning_pairs_kernel(uint32_t* buf0, uint32_t* buf1, uint32_t* val0, uint3
     }
     __syncthreads();
 
-    // ---- chained scan, BEFORE the rank phase: the digit warps look back while the other warps already rank, and no
-    // lookback state competes with the remembered slots for registers later on ------------------------------------
-    if (tid < kRadix) {
-        TileRereduce<KeyT> rr;
-        rr.in = (sm.plan_bits & 1u) ? buf1 : buf0; rr.tile_keys = T; rr.shift = shift; rr.mask = dmask;
-        rr.encode = (sm.plan_bits >> 1) & kCodecEncodeOnLoad;
-        rr.ca = static_cast<KeyT>(codec.a); rr.cb = static_cast<KeyT>(codec.b); rr.cd = static_cast<KeyT>(codec.d);
-        const unsigned long long prior = lookback_wide<LOOK, STEP, KeyT>(agg16, incl64, tile, tid, epoch, pp.spin_cap, rr);
-        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid, desc_pack(epoch, kFlagInclusive, prior + tile_count));
-        const bool swap = sm.plan_bits & 1u;
-        const unsigned long long first = gbase[tid] + prior - tile_excl;
-        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(swap ? buf0 : buf1) + first * sizeof(KeyT);
-        sm.valptr[tid] = reinterpret_cast<unsigned long long>(swap ? val0 : val1) + first * sizeof(uint32_t);
-    }
     // ---- rank: keys to their slots; the slots are kept for the payloads --------------------------------------
     uint32_t slots[K / 2];
 #pragma unroll
@@ -1121,6 +1229,31 @@ digit_binning_pairs_kernel(uint32_t* buf0, uint32_t* buf1, uint32_t* val0, uint3
         const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift, dmask), lt);
         sm.sorted[slot] = key[i];
         if (i & 1) slots[i / 2] |= slot << 16; else slots[i / 2] = slot;
+    }
+    // ---- chained scan, AFTER the rank phase (as in digit_binning_wide_kernel): the keys are dead by now, so nothing of
+    // theirs is spilled around the lookback, and no warp of this CTA ranks while the lookback's loads are in flight.  (Round 2:
+    // with the lookback ahead of the rank phase a build of this kernel produced rare order violations inside single warps at
+    // n >= 2^28 -- profiles/r02_pairs_order_violation.md; the cause was not pinned down, this order has never shown one.)
+    if (tid < kRadix) {
+        TileRereduce<KeyT> rr;
+        rr.in = (sm.plan_bits & 1u) ? buf1 : buf0; rr.tile_keys = T; rr.shift = shift; rr.mask = dmask;
+        rr.encode = (sm.plan_bits >> 1) & kCodecEncodeOnLoad;
+        rr.ca = static_cast<KeyT>(codec.a); rr.cb = static_cast<KeyT>(codec.b); rr.cd = static_cast<KeyT>(codec.d);
+        const unsigned long long prior = lookback_wide<LOOK / 8, KeyT>(agg16, incl64, tile, tid, epoch, pp.spin_cap, rr);
+#if OSB_EXP & 128
+        if (tile > 0) {  // (development) cross-check against the predecessor's inclusive prefix
+            uint64_t w;
+            do { w = ld_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile - 1) * kRadix + tid); } while (desc_epoch(w) != epoch || (w & kFlagMask) != kFlagInclusive);
+            if (desc_value(w) != prior && atomicAdd(&g_phase[11], 1ull) == 0) {
+                g_phase[12] = tile; g_phase[13] = tid; g_phase[14] = prior; g_phase[15] = desc_value(w);
+            }
+        }
+#endif
+        st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid, desc_pack(epoch, kFlagInclusive, prior + tile_count));
+        const bool swap = sm.plan_bits & 1u;
+        const unsigned long long first = gbase[tid] + prior - tile_excl;
+        sm.keyptr[tid] = reinterpret_cast<unsigned long long>(swap ? buf0 : buf1) + first * sizeof(KeyT);
+        sm.valptr[tid] = reinterpret_cast<unsigned long long>(swap ? val0 : val1) + first * sizeof(uint32_t);
     }
     __syncthreads();
 
@@ -1208,9 +1341,17 @@ struct RingSmem {
     uint32_t wtot[kRadix / 32];
 };
 
-#ifndef OSB_LOOK  // overridable for parameter sweeps (tools/sweep.sh)
-#define OSB_LOOK 8
-#define OSB_STEP 4
+// Lookback window in tiles (a multiple of 8: whole blocks of reductions, one inclusive probe per block); overridable for
+// parameter sweeps (tools/sweep.sh).  OSB_STEP is kept only as a template argument of the kernels (unused since the probes
+// follow the blocks).
+#ifndef OSB_LOOK
+#define OSB_LOOK 16
+#endif
+#ifndef OSB_STEP
+#define OSB_STEP 8
+#endif
+#ifndef OSB_PAIRS_LOOK  // the pairs kernel looks back with its 32 keys still in registers: a narrower window
+#define OSB_PAIRS_LOOK 16
 #endif
 #ifndef OSB_RING_K  // u32 geometry of the ring kernel, overridable for sweeps: keys per thread, resident CTAs per SM
 #define OSB_RING_K 16
@@ -1290,7 +1431,7 @@ digit_binning_ring_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, u
         if (tid < kRadix) {
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
-            st_relaxed_gpu_u16(agg16 + static_cast<uint64_t>(tile) * kRadix + tid, kAggReady | tile_count);
+            st_relaxed_gpu_u16(agg16 + agg_index(tile, tid), kAggReady | tile_count);
         }
         tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
         if (tid < kRadix) {
@@ -1308,7 +1449,7 @@ digit_binning_ring_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, u
             TileRereduce<KeyT> rr;
             rr.in = in; rr.tile_keys = T; rr.shift = shift; rr.mask = kRadix - 1; rr.encode = false;
             rr.ca = rr.cb = rr.cd = 0;
-            const unsigned long long prior = lookback_wide<LOOK, STEP, KeyT>(agg16, incl64, tile, tid, epoch, 1u << 20, rr);
+            const unsigned long long prior = lookback_wide<LOOK / 8, KeyT>(agg16, incl64, tile, tid, epoch, 1u << 20, rr);
             st_relaxed_gpu_u64(incl64 + static_cast<uint64_t>(tile) * kRadix + tid,
                                desc_pack(epoch, kFlagInclusive, prior + tile_count));
             sm.keyptr[tid] = reinterpret_cast<unsigned long long>(out) + (gbase[tid] + prior - tile_excl) * sizeof(KeyT);
@@ -1345,7 +1486,7 @@ digit_binning_ring_kernel(const KeyT* __restrict__ in, KeyT* __restrict__ out, u
 
 template <typename KeyT> struct RingGeom;
 template <> struct RingGeom<uint32_t> { static constexpr int K = OSB_RING_K, WARPS = 16, LOOK = OSB_LOOK, STEP = OSB_STEP; };
-template <> struct RingGeom<uint64_t> { static constexpr int K = 8,  WARPS = 16, LOOK = 16, STEP = 8; };
+template <> struct RingGeom<uint64_t> { static constexpr int K = 8,  WARPS = 16, LOOK = OSB_LOOK, STEP = OSB_STEP; };
 
 template <typename KeyT, int RANK_MODE>
 static cudaError_t launch_ring_variant(const void* in, void* out, uint64_t n, uint32_t shift, const unsigned long long* gbase,
@@ -1433,7 +1574,7 @@ static cudaError_t launch_pairs_variant(const void* in, void* out, const uint32_
     pp.spin_cap = cfg.spin_cap;
     pp.stall_every = cfg.debug_stall_every;
     pp.plan = cfg.plan;
-    auto kern = digit_binning_pairs_kernel<kPairsK, kPairsWarps, RANK_MODE, OSB_LOOK, OSB_STEP>;
+    auto kern = digit_binning_pairs_kernel<kPairsK, kPairsWarps, RANK_MODE, OSB_PAIRS_LOOK, OSB_STEP>;
     kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
         static_cast<uint32_t*>(const_cast<void*>(in)), static_cast<uint32_t*>(out), const_cast<uint32_t*>(in_val), out_val, n,
         gbase, agg16, incl64, ticket, pp, cfg.codec);
@@ -1444,7 +1585,7 @@ template <int RANK_MODE>
 static cudaError_t set_pairs_attr()
 {
     using S = PairsSmem<kPairsWarps, kPairsK>;
-    return cudaFuncSetAttribute(digit_binning_pairs_kernel<kPairsK, kPairsWarps, RANK_MODE, OSB_LOOK, OSB_STEP>,
+    return cudaFuncSetAttribute(digit_binning_pairs_kernel<kPairsK, kPairsWarps, RANK_MODE, OSB_PAIRS_LOOK, OSB_STEP>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
 }
 
