@@ -31,6 +31,7 @@ SIGNATURES = {
     "osb200_sort_keys_typed": (c_int, [c_vp, c_vp, c_u64, c_int, c_int, c_vp]),
     "osb200_sort_pairs_typed": (c_int, [c_vp, c_vp, c_vp, c_u64, c_int, c_int, c_vp]),
     "osb200_sort_bits": (c_int, [c_vp, c_vp, c_vp, c_u64, c_int, c_int, c_vp]),
+    "osb200_segmented_sort_u32": (c_int, [c_vp, c_vp, c_vp, c_vp, c_u64, ctypes.c_uint32, c_vp]),
     "osb200_sort_host_keys_u32": (c_int, [c_vp, c_vp, c_u64]),
     "osb200_sort_host_pairs_u32": (c_int, [c_vp, c_vp, c_vp, c_u64]),
     "osb200_sort_host_keys_u64": (c_int, [c_vp, c_vp, c_u64]),

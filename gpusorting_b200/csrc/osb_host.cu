@@ -54,6 +54,7 @@ struct osb200_sorter {
     osb::BinningConfig cfg;
     bool atomic_order_ok = false;
     bool short_circuit = true;   // skip passes whose digit is the same for all keys (decided on the device, no host sync)
+    bool small_path = true;      // n <= one tile: the single-CTA shared-memory sort (one launch)
 
     void* alt_keys = nullptr;
     uint32_t* alt_vals = nullptr;
@@ -139,6 +140,17 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
     // the device plan (pass skipping, odd pass counts, bit ranges) is a feature of the default kernel
     if (!wide && !whole_key) return OSB200_ERR_UNSUPPORTED;
     const bool use_plan = wide;
+
+    // small-n path: up to one tile of keys is sorted by ONE CTA in shared memory, one launch
+    if (wide && s->small_path && n <= osb::segment_sort_capacity(s->key_bytes, false)) {
+        osb::KeyCodec c;
+        if (codec) { c = *codec; c.flags = osb::kCodecEncodeOnLoad | osb::kCodecDecodeOnStore; }
+        s->ev_count = 0;
+        OSB_TRY(osb::launch_segment_sort(d_keys, d_vals, s->key_bytes, nullptr, 1, n, static_cast<uint32_t>(n),
+                                         static_cast<uint32_t>(begin_bit), static_cast<uint32_t>(places), last_bits,
+                                         codec ? &c : nullptr, s->cfg.rank_mode, s->sm_count, stream));
+        return OSB200_OK;
+    }
 
     OSB_TRY(cudaMemsetAsync(s->control, 0, ControlLayout::zeroed_bytes, stream));
     const bool compact = s->cfg.variant != osb::kVariantTilePerCta;  // every other variant uses the compact reductions
@@ -408,6 +420,20 @@ int osb200_sort_keys_typed(osb200_handle h, void* d_keys, uint64_t n, int key_ty
     return sort_impl(h, d_keys, nullptr, n, static_cast<cudaStream_t>(stream), plain ? nullptr : &c);
 }
 
+int osb200_segmented_sort_u32(osb200_handle h, uint32_t* d_keys, uint32_t* d_values, const uint64_t* d_segment_offsets,
+                              uint64_t num_segments, uint32_t max_segment_len, void* stream)
+{
+    if (check_handle(h) != OSB200_OK) return OSB200_ERR_INVALID_ARG;
+    if (h->key_bytes != 4 || (d_values && h->value_bytes != 4)) return OSB200_ERR_INVALID_ARG;
+    if (num_segments == 0 || max_segment_len <= 1) return OSB200_OK;
+    if (!d_keys || !d_segment_offsets) return OSB200_ERR_INVALID_ARG;
+    if (max_segment_len > osb::segment_sort_capacity(4, false)) return OSB200_ERR_SIZE;  // sort longer segments with osb200_sort_*
+    OSB_TRY(osb::launch_segment_sort(d_keys, d_values, 4, reinterpret_cast<const unsigned long long*>(d_segment_offsets), num_segments,
+                                     0, max_segment_len, 0, 4, 8, nullptr, h->cfg.rank_mode, h->sm_count,
+                                     static_cast<cudaStream_t>(stream)));
+    return OSB200_OK;
+}
+
 int osb200_sort_bits(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int begin_bit, int end_bit, void* stream)
 {
     if (check_handle(h) != OSB200_OK) return OSB200_ERR_INVALID_ARG;
@@ -526,6 +552,7 @@ int osb200_set_option(osb200_handle h, const char* key, int64_t value)
     }
     if (!std::strcmp(key, "profile")) { h->profile = value != 0; return OSB200_OK; }
     if (!std::strcmp(key, "short_circuit")) { h->short_circuit = value != 0; return OSB200_OK; }
+    if (!std::strcmp(key, "small_path")) { h->small_path = value != 0; return OSB200_OK; }
     if (!std::strcmp(key, "spin_cap")) {
         if (value < 1 || value > (1ll << 30)) return OSB200_ERR_INVALID_ARG;
         h->cfg.spin_cap = static_cast<uint32_t>(value);
@@ -564,6 +591,8 @@ int64_t osb200_get_info(osb200_handle h, const char* key)
     }
     if (!std::strcmp(key, "memsets_per_sort")) return h->cfg.variant != osb::kVariantTilePerCta ? 2 : 1;
     if (!std::strcmp(key, "short_circuit")) return h->short_circuit ? 1 : 0;
+    if (!std::strcmp(key, "small_path")) return h->small_path ? 1 : 0;
+    if (!std::strcmp(key, "small_path_max_n")) return osb::segment_sort_capacity(h->key_bytes, false);
     if (!std::strcmp(key, "spin_cap")) return h->cfg.spin_cap;
     if (!std::strcmp(key, "last_skip_mask") || !std::strcmp(key, "last_executed_passes")) {
         // the plan of the last sort on this handle (synchronises the device: introspection / tests only)

@@ -1650,6 +1650,8 @@ static cudaError_t set_tile_attr()
                                 static_cast<int>(tile_smem_bytes<KeyT, PAIRS>()));
 }
 
+static cudaError_t configure_segment_kernels();
+
 cudaError_t configure_kernels()
 {
     cudaError_t e;
@@ -1679,7 +1681,7 @@ cudaError_t configure_kernels()
     if ((e = set_wide_attr<uint64_t, false, kRankBallot>()) != cudaSuccess) return e;
     if ((e = set_pairs_attr<kRankAtomic>()) != cudaSuccess) return e;
     if ((e = set_pairs_attr<kRankBallot>()) != cudaSuccess) return e;
-    return cudaSuccess;
+    return configure_segment_kernels();
 }
 
 cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
@@ -1724,6 +1726,190 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
     if (key_bytes == 4) return pairs ? OSB_DISPATCH(uint32_t, true) : OSB_DISPATCH(uint32_t, false);
     if (key_bytes == 8 && !pairs) return OSB_DISPATCH(uint64_t, false);
 #undef OSB_DISPATCH
+    return cudaErrorInvalidValue;
+}
+
+// =====================================================================================================
+// Segment sort / small-n path: ONE CTA sorts ONE segment of at most T keys entirely in shared memory (all digit passes:
+// count, scan, rank, read back), one launch, no global histogram, no descriptors, no lookback.
+//
+// Reference: the reference's other contribution, SplitSort (SegSort/SplitSort/SplitSort.cuh:702-938), sorts many short
+// segments by binning them by length; and a OneSweep::Sort of n < ~2^16 keys is launch-bound (6 launches + memsets,
+// SURVEY 8f rank 4).  Here both are the same kernel: osb200_segmented_sort_u32 runs it over an array of segment offsets
+// (grid-stride over the segments), and every osb200_sort_* call with n <= T takes it as its single segment [0, n).
+// The ranking is the DigitBinningPass's (warp-private histograms, returning atomic = slot), so the sort is stable and typed
+// keys / bit ranges cost nothing extra.  Segments longer than T are not this kernel's business (the caller sorts them with
+// the ordinary path).
+// =====================================================================================================
+template <typename KeyT, bool PAIRS, int K, int WARPS>
+struct SegSmem {
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int T = THREADS * K;
+    alignas(16) KeyT sorted[T];
+    alignas(16) uint32_t sorted_val[PAIRS ? T : 4];
+    alignas(16) uint32_t hist[WARPS * kRadix];
+    uint32_t wtot[kRadix / 32];
+};
+
+template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE>
+__global__ void __launch_bounds__(WARPS * 32)
+segment_sort_kernel(KeyT* keys, uint32_t* vals, const unsigned long long* __restrict__ seg_off, uint64_t num_segments,
+                    uint64_t single_n, uint32_t begin_bit, uint32_t places, uint32_t last_bits, KeyCodec codec)
+{
+    using S = SegSmem<KeyT, PAIRS, K, WARPS>;
+    constexpr int THREADS = S::THREADS;
+    constexpr int T = S::T;
+    static_assert(WARPS >= 8, "one thread per digit");
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    S& sm = *reinterpret_cast<S*>(s_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = lanemask_lt();
+    uint32_t* wh = sm.hist + warp * kRadix;
+    const uint32_t warp_off = warp * (32 * K) + lane;
+    const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
+    const bool enc = codec.flags & kCodecEncodeOnLoad, dec = codec.flags & kCodecDecodeOnStore;
+
+    for (uint64_t seg = blockIdx.x; seg < num_segments; seg += gridDim.x) {
+        const uint64_t lo = seg_off ? seg_off[seg] : 0ull;
+        const uint64_t hi = seg_off ? seg_off[seg + 1] : single_n;
+        if (hi <= lo + 1 || hi - lo > static_cast<uint64_t>(T)) continue;  // empty / one key / too long (caller's contract)
+        const uint32_t len = static_cast<uint32_t>(hi - lo);
+
+        KeyT key[K];
+        uint32_t val[PAIRS ? K : 1];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const uint32_t idx = warp_off + i * 32;
+            KeyT k = idx < len ? keys[lo + idx] : static_cast<KeyT>(0);
+            if (enc) k = codec_encode<KeyT>(k, ca, cb, cd);
+            key[i] = idx < len ? k : static_cast<KeyT>(~static_cast<KeyT>(0));  // padding ranks last in every pass
+            if constexpr (PAIRS) val[i] = idx < len ? vals[lo + idx] : 0u;
+        }
+
+        for (uint32_t p = 0; p < places; ++p) {
+            const uint32_t shift = begin_bit + 8u * p;
+            const uint32_t dmask = p == places - 1 ? (1u << last_bits) - 1u : 255u;
+            __syncthreads();  // the previous pass (or segment) has read the tile back
+            {
+                uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+                for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < K; ++i) atomicAdd(&wh[digit_of(key[i], shift, dmask)], 1u);
+            __syncthreads();
+            uint32_t tile_count = 0;
+            if (tid < kRadix) {
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) tile_count += sm.hist[w * kRadix + tid];
+            }
+            const uint32_t tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
+            if (tid < kRadix) {
+                uint32_t run = tile_excl;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) { const uint32_t c = sm.hist[w * kRadix + tid]; sm.hist[w * kRadix + tid] = run; run += c; }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift, dmask), lt);
+                sm.sorted[slot] = key[i];
+                if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
+            }
+            __syncthreads();
+            if (p + 1 < places) {  // back into registers in tile order for the next digit
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    key[i] = sm.sorted[warp_off + i * 32];
+                    if constexpr (PAIRS) val[i] = sm.sorted_val[warp_off + i * 32];
+                }
+            }
+        }
+        // the padding sits behind the `len` real keys
+        for (uint32_t idx = tid; idx < len; idx += THREADS) {
+            KeyT k = sm.sorted[idx];
+            if (dec) k = codec_decode<KeyT>(k, ca, cb, cd);
+            keys[lo + idx] = k;
+            if constexpr (PAIRS) vals[lo + idx] = sm.sorted_val[idx];
+        }
+    }
+}
+
+// three geometries per key type (SIZE 0 / 1 / 2): tiny and short segments (many resident CTAs; the work per segment is
+// proportional to the geometry's capacity, padding included) and up to a DigitBinningPass tile
+template <typename KeyT, int SIZE> struct SegGeomN;
+template <> struct SegGeomN<uint32_t, 0> { static constexpr int K = 1,  WARPS = 8; };   //    256 keys, 256 threads
+template <> struct SegGeomN<uint32_t, 1> { static constexpr int K = 8,  WARPS = 8; };   //  2,048 keys, 256 threads
+template <> struct SegGeomN<uint32_t, 2> { static constexpr int K = 32, WARPS = 16; };  // 16,384 keys, 512 threads
+template <> struct SegGeomN<uint64_t, 0> { static constexpr int K = 1,  WARPS = 8; };   //    256 keys
+template <> struct SegGeomN<uint64_t, 1> { static constexpr int K = 8,  WARPS = 8; };   //  2,048 keys
+template <> struct SegGeomN<uint64_t, 2> { static constexpr int K = 16, WARPS = 16; };  //  8,192 keys
+template <typename KeyT, int SIZE> constexpr uint32_t seg_cap() { return SegGeomN<KeyT, SIZE>::K * SegGeomN<KeyT, SIZE>::WARPS * 32; }
+
+uint32_t segment_sort_capacity(int key_bytes, bool small)
+{
+    if (key_bytes == 8) return small ? seg_cap<uint64_t, 1>() : seg_cap<uint64_t, 2>();
+    return small ? seg_cap<uint32_t, 1>() : seg_cap<uint32_t, 2>();
+}
+
+template <typename KeyT, bool PAIRS, int SIZE, int RANK_MODE>
+static cudaError_t seg_attr()
+{
+    using G = SegGeomN<KeyT, SIZE>;
+    return cudaFuncSetAttribute(segment_sort_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(sizeof(SegSmem<KeyT, PAIRS, G::K, G::WARPS>)));
+}
+static cudaError_t configure_segment_kernels()
+{
+    cudaError_t e;
+#define OSB_SEG_ATTR(KEYT, PAIRS)                                                                          \
+    if ((e = seg_attr<KEYT, PAIRS, 0, kRankAtomic>()) != cudaSuccess) return e;                             \
+    if ((e = seg_attr<KEYT, PAIRS, 0, kRankBallot>()) != cudaSuccess) return e;                             \
+    if ((e = seg_attr<KEYT, PAIRS, 1, kRankAtomic>()) != cudaSuccess) return e;                             \
+    if ((e = seg_attr<KEYT, PAIRS, 1, kRankBallot>()) != cudaSuccess) return e;                             \
+    if ((e = seg_attr<KEYT, PAIRS, 2, kRankAtomic>()) != cudaSuccess) return e;                             \
+    if ((e = seg_attr<KEYT, PAIRS, 2, kRankBallot>()) != cudaSuccess) return e;
+    OSB_SEG_ATTR(uint32_t, false)
+    OSB_SEG_ATTR(uint32_t, true)
+    OSB_SEG_ATTR(uint64_t, false)
+#undef OSB_SEG_ATTR
+    return cudaSuccess;
+}
+
+template <typename KeyT, bool PAIRS, int SIZE>
+static cudaError_t launch_seg(void* keys, uint32_t* vals, const unsigned long long* seg_off, uint64_t num_segments, uint64_t single_n,
+                              uint32_t begin_bit, uint32_t places, uint32_t last_bits, const KeyCodec& codec, int rank_mode, int sm_count,
+                              cudaStream_t stream)
+{
+    using G = SegGeomN<KeyT, SIZE>;
+    using S = SegSmem<KeyT, PAIRS, G::K, G::WARPS>;
+    const uint64_t cap = static_cast<uint64_t>(sm_count) * (SIZE == 2 ? 2 : 8);
+    const unsigned grid = static_cast<unsigned>(num_segments < cap ? num_segments : cap);
+    if (rank_mode == kRankBallot)
+        segment_sort_kernel<KeyT, PAIRS, G::K, G::WARPS, kRankBallot><<<grid, S::THREADS, sizeof(S), stream>>>(
+            static_cast<KeyT*>(keys), vals, seg_off, num_segments, single_n, begin_bit, places, last_bits, codec);
+    else
+        segment_sort_kernel<KeyT, PAIRS, G::K, G::WARPS, kRankAtomic><<<grid, S::THREADS, sizeof(S), stream>>>(
+            static_cast<KeyT*>(keys), vals, seg_off, num_segments, single_n, begin_bit, places, last_bits, codec);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_segment_sort(void* keys, uint32_t* vals, int key_bytes, const unsigned long long* seg_off, uint64_t num_segments,
+                                uint64_t single_n, uint32_t max_len, uint32_t begin_bit, uint32_t places, uint32_t last_bits,
+                                const KeyCodec* codec_in, int rank_mode, int sm_count, cudaStream_t stream)
+{
+    if (num_segments == 0) return cudaSuccess;
+    const KeyCodec codec = codec_in ? *codec_in : KeyCodec();
+    const int size = max_len <= (key_bytes == 8 ? seg_cap<uint64_t, 0>() : seg_cap<uint32_t, 0>()) ? 0
+                     : max_len <= segment_sort_capacity(key_bytes, true) ? 1 : 2;
+    if (max_len > segment_sort_capacity(key_bytes, false)) return cudaErrorInvalidValue;
+#define OSB_SEG_ARGS keys, vals, seg_off, num_segments, single_n, begin_bit, places, last_bits, codec, rank_mode, sm_count, stream
+#define OSB_SEG(KEYT, PAIRS) \
+    (size == 0 ? launch_seg<KEYT, PAIRS, 0>(OSB_SEG_ARGS) : size == 1 ? launch_seg<KEYT, PAIRS, 1>(OSB_SEG_ARGS) : launch_seg<KEYT, PAIRS, 2>(OSB_SEG_ARGS))
+    if (key_bytes == 4) return vals ? OSB_SEG(uint32_t, true) : OSB_SEG(uint32_t, false);
+    if (key_bytes == 8 && !vals) return OSB_SEG(uint64_t, false);
+#undef OSB_SEG_ARGS
+#undef OSB_SEG
     return cudaErrorInvalidValue;
 }
 

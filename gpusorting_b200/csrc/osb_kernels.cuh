@@ -73,6 +73,14 @@ cudaError_t launch_digit_binning(const void* in, void* out, const uint32_t* in_v
                                  uint16_t* agg16, uint32_t* ticket, uint32_t epoch, const BinningConfig& cfg,
                                  cudaStream_t stream);
 
+// Segment sort / small-n path: one CTA sorts one segment (<= segment_sort_capacity keys) in shared memory, all digit passes
+// in one launch.  seg_off == nullptr: the single segment [0, single_n).  max_len (an upper bound of the segment lengths)
+// picks the geometry; segments longer than the capacity are skipped by the kernel (the caller must not pass them).
+uint32_t segment_sort_capacity(int key_bytes, bool small);
+cudaError_t launch_segment_sort(void* keys, uint32_t* vals, int key_bytes, const unsigned long long* seg_off, uint64_t num_segments,
+                                uint64_t single_n, uint32_t max_len, uint32_t begin_bit, uint32_t places, uint32_t last_bits,
+                                const KeyCodec* codec, int rank_mode, int sm_count, cudaStream_t stream);
+
 // Validate (reference: Validate, UtilityKernels.cuh:403-429): err_count += #(keys[i] > keys[i+1]).
 cudaError_t launch_validate(const void* keys, uint64_t n, int key_bytes, unsigned long long* err_count, int sm_count,
                             cudaStream_t stream);

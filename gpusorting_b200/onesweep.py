@@ -150,6 +150,28 @@ class OneSweepSorter:
                                        int(begin_bit), int(end_bit), _stream_ptr(stream)), "osb200_sort_bits")
         return keys if values is None else (keys, values)
 
+    def segmented_sort(self, keys: torch.Tensor, segment_offsets: torch.Tensor, values: Optional[torch.Tensor] = None,
+                       max_segment_len: Optional[int] = None, stream=None):
+        """Sort every segment [offsets[i], offsets[i+1]) of `keys` (and `values`) ascending and stable, in place, one thread
+        block per segment (osb200_segmented_sort_u32; reference: SplitSort, SegSort/SplitSort/SplitSort.cuh:702-938).
+        `segment_offsets`: int64 device tensor of num_segments + 1 offsets.  `max_segment_len` (default: computed here, which
+        costs a device->host read) must not exceed 16,384."""
+        _check_dev_tensor(keys, _KEY_DTYPES_4, "keys", keys.numel(), self.device)
+        if values is not None:
+            _check_dev_tensor(values, _TYPED_DTYPES_4, "values", keys.numel(), self.device)
+        if segment_offsets.dtype != torch.int64 or not segment_offsets.is_cuda or not segment_offsets.is_contiguous():
+            raise TypeError("segment_offsets must be a contiguous int64 CUDA tensor")
+        segs = segment_offsets.numel() - 1
+        if segs <= 0:
+            return keys if values is None else (keys, values)
+        if max_segment_len is None:
+            max_segment_len = int((segment_offsets[1:] - segment_offsets[:-1]).max().item())
+        with torch.cuda.device(self.device):
+            check(lib.osb200_segmented_sort_u32(self._h, keys.data_ptr(), values.data_ptr() if values is not None else None,
+                                                segment_offsets.data_ptr(), segs, int(max_segment_len), _stream_ptr(stream)),
+                  "osb200_segmented_sort_u32")
+        return keys if values is None else (keys, values)
+
     def sort_pairs(self, keys: torch.Tensor, values: torch.Tensor, n: Optional[int] = None, stream=None):
         n = keys.numel() if n is None else int(n)
         _check_dev_tensor(keys, _KEY_DTYPES_4, "keys", n, self.device)

@@ -105,6 +105,18 @@ OSB200_API int osb200_sort_pairs_typed(osb200_handle h, void* d_keys, uint32_t* 
 OSB200_API int osb200_sort_bits(osb200_handle h, void* d_keys, uint32_t* d_values, uint64_t n, int begin_bit, int end_bit,
                                 void* stream);
 
+/* Segmented sort: every segment [offsets[i], offsets[i+1]) of d_keys (and d_values, may be NULL) is sorted ascending and
+ * stable, in place, by ONE thread block in shared memory (all four digit passes in one launch; no histogram, descriptor or
+ * lookback traffic).  d_segment_offsets: num_segments + 1 non-decreasing element offsets in device memory.
+ * max_segment_len: an upper bound of the segment lengths known to the caller; it picks the block geometry (<= 256 or 2,048 keys:
+ * 256 threads, up to 8 blocks per SM; <= 16,384: 512 threads) -- segments longer than 16,384 keys return OSB200_ERR_SIZE
+ * (sort those with osb200_sort_*), segments longer than max_segment_len are left untouched.  Empty segments are fine.
+ * Reference: SplitSort, the reference's segmented sort (GPUSortingCUDA/SegSort/SplitSort/SplitSort.cuh:702-938 bins
+ * segments by length and dispatches one kernel per bin); SURVEY 8f rank 4.  The same kernel is the small-n path of every
+ * osb200_sort_* call: n <= 16,384 (8,192 for 64-bit keys) is one segment, one launch (option "small_path", default 1). */
+OSB200_API int osb200_segmented_sort_u32(osb200_handle h, uint32_t* d_keys, uint32_t* d_values, const uint64_t* d_segment_offsets,
+                                         uint64_t num_segments, uint32_t max_segment_len, void* stream);
+
 /* Host-buffer entry points: copy in, sort, copy back, synchronise.  `h_*` may be pageable or pinned
  * host memory.  This is the end-to-end call a host-side caller of the reference would make (the
  * reference itself has no host-data API; its buffers are generated on the device,

@@ -102,11 +102,13 @@ def test_init_random_matches_oracle(g, oracle):
         assert np.array_equal(host_u32(t), oracle.init_random_u32(n, andc, seed))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant,small", [(0, 1), (1, 1), (2, 1), (2, 0)])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_keys_u32_edge_sizes(sorter, oracle, mode, variant):
+def test_keys_u32_edge_sizes(sorter, oracle, mode, variant, small):
+    """small = 0: n <= one tile goes through the ordinary kernels too (the single-CTA small-n path is switched off)"""
     sorter.set_option("rank_mode", mode)
     sorter.set_option("variant", variant)
+    sorter.set_option("small_path", small)
     T = tile_keys(sorter)
     sizes = [0, 1, 2, 3, 31, 32, 33, 255, 256, 257, 1000, T - 1, T, T + 1, 2 * T - 1, 2 * T, 2 * T + 1, 3 * T + 17, 100003]
     try:
@@ -115,14 +117,15 @@ def test_keys_u32_edge_sizes(sorter, oracle, mode, variant):
             t = torch.empty(max(n, 4), dtype=torch.int32, device="cuda")
             t[:n] = dev_u32(k)
             sorter.sort_keys(t, n)
-            assert np.array_equal(host_u32(t[:n]), oracle.sort_keys(k)), f"n={n} mode={mode} variant={variant}"
+            assert np.array_equal(host_u32(t[:n]), oracle.sort_keys(k)), f"n={n} mode={mode} variant={variant} small={small}"
     finally:
         sorter.set_option("rank_mode", 0)
         sorter.set_option("variant", DEFAULT_VARIANT)
+        sorter.set_option("small_path", 1)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
-def test_reference_size_sweep(sorter, oracle, variant):
+@pytest.mark.parametrize("variant,small", [(0, 1), (1, 1), (2, 1), (2, 0)])
+def test_reference_size_sweep(sorter, oracle, variant, small):
     """The reference's TestAllKeysOnly sweep shape (OneSweepDispatcher.cuh:98-113): sizes across one..two of ITS
     tiles (7680..15360) and across one..two of OUR tiles, seed = n, checked bit-exactly (the reference only
     checks sortedness)."""
@@ -130,6 +133,7 @@ def test_reference_size_sweep(sorter, oracle, variant):
     sizes = list(range(7680, 15361, 193)) + list(range(T, 2 * T + 1, 331))
     buf = torch.empty(max(sizes), dtype=torch.int32, device="cuda")
     sorter.set_option("variant", variant)
+    sorter.set_option("small_path", small)
     try:
         for n in sizes:
             k = oracle.init_random_u32(n, 0, n)
@@ -138,6 +142,7 @@ def test_reference_size_sweep(sorter, oracle, variant):
             assert np.array_equal(host_u32(buf[:n]), oracle.sort_keys(k)), f"n={n}"
     finally:
         sorter.set_option("variant", DEFAULT_VARIANT)
+        sorter.set_option("small_path", 1)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2])
@@ -300,12 +305,14 @@ def test_error_behaviour(g, sorter):
 def test_repeated_sorts_reuse_descriptors_without_clearing(sorter, oracle):
     """Epoch-stamped descriptors: many sorts of different sizes back to back on one handle, no memsets."""
     e0 = sorter.info("epoch")
-    for i, n in enumerate([50000, 1 << 20, 777, 1 << 19, 50001] * 3):
+    sizes = [50000, 1 << 20, 777, 1 << 19, 50001] * 3
+    for i, n in enumerate(sizes):
         k = oracle.init_random_u32(n, i % 3, 5 + i)
         t = dev_u32(k)
         sorter.sort_keys(t)
         assert np.array_equal(host_u32(t), oracle.sort_keys(k))
-    assert sorter.info("epoch") == e0 + 15 * 4
+    # one epoch per DigitBinningPass launch; a sort of at most one tile takes the single-CTA path and launches none
+    assert sorter.info("epoch") == e0 + 4 * sum(n > sorter.info("small_path_max_n") for n in sizes)
 
 
 def test_sort_on_side_stream_and_module_level_Sort(g, oracle):
