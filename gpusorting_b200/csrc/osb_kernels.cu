@@ -32,8 +32,10 @@ template <typename KeyT> struct HistGeom;
 template <> struct HistGeom<uint32_t> { static constexpr int COLS = 32; };
 template <> struct HistGeom<uint64_t> { static constexpr int COLS = 16; };
 
-template <typename KeyT>
-__device__ __forceinline__ void hist_count_word(uint32_t* s_col, uint32_t w, int word_in_vec)
+// MASKED: a sort on the key bits [0, end_bit) -- only the first `places` byte places count and the last of them keeps
+// `last_mask` (the sharded path's local sort after an exchange on the top log2(R) bits: bits [0, 32 - log2 R))
+template <typename KeyT, bool MASKED = false>
+__device__ __forceinline__ void hist_count_word(uint32_t* s_col, uint32_t w, int word_in_vec, int places = 0, uint32_t last_mask = 255u)
 {
     constexpr int PLACES = sizeof(KeyT);
     constexpr int COLS = HistGeom<KeyT>::COLS;
@@ -41,7 +43,12 @@ __device__ __forceinline__ void hist_count_word(uint32_t* s_col, uint32_t w, int
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int place = (word_in_vec * 4 + q) % PLACES;
-        atomicAdd(&s_col[(place * kRadix + ((w >> (8 * q)) & 255u)) * COLS], 1u);
+        if constexpr (MASKED) {
+            if (place < places)
+                atomicAdd(&s_col[(place * kRadix + ((w >> (8 * q)) & (place == places - 1 ? last_mask : 255u))) * COLS], 1u);
+        } else {
+            atomicAdd(&s_col[(place * kRadix + ((w >> (8 * q)) & 255u)) * COLS], 1u);
+        }
     }
 }
 
@@ -61,18 +68,19 @@ __device__ __forceinline__ uint4 hist_encode_vec(uint4 v, const KeyCodec& c)
     return v;
 }
 
-template <typename KeyT>
-__device__ __forceinline__ void hist_count_vec(uint32_t* s_col, const uint4& v)
+template <typename KeyT, bool MASKED = false>
+__device__ __forceinline__ void hist_count_vec(uint32_t* s_col, const uint4& v, int places = 0, uint32_t last_mask = 255u)
 {
-    hist_count_word<KeyT>(s_col, v.x, 0);
-    hist_count_word<KeyT>(s_col, v.y, 1);
-    hist_count_word<KeyT>(s_col, v.z, 2);
-    hist_count_word<KeyT>(s_col, v.w, 3);
+    hist_count_word<KeyT, MASKED>(s_col, v.x, 0, places, last_mask);
+    hist_count_word<KeyT, MASKED>(s_col, v.y, 1, places, last_mask);
+    hist_count_word<KeyT, MASKED>(s_col, v.z, 2, places, last_mask);
+    hist_count_word<KeyT, MASKED>(s_col, v.w, 3, places, last_mask);
 }
 
-template <typename KeyT>
+template <typename KeyT, bool MASKED = false>
 __global__ void __launch_bounds__(kHistThreads, 1)
-global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ ghist, KeyCodec codec)
+global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ ghist, KeyCodec codec,
+                        int places = 0, uint32_t last_mask = 255u)
 {
     constexpr int PLACES = sizeof(KeyT);
     constexpr int VEC = 16 / sizeof(KeyT);
@@ -94,15 +102,15 @@ global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long
         uint4 c = __ldcs(vp + i + 2 * stride);
         uint4 d = __ldcs(vp + i + 3 * stride);
         if (enc) { a = hist_encode_vec<KeyT>(a, codec); b = hist_encode_vec<KeyT>(b, codec); c = hist_encode_vec<KeyT>(c, codec); d = hist_encode_vec<KeyT>(d, codec); }
-        hist_count_vec<KeyT>(s_col, a);
-        hist_count_vec<KeyT>(s_col, b);
-        hist_count_vec<KeyT>(s_col, c);
-        hist_count_vec<KeyT>(s_col, d);
+        hist_count_vec<KeyT, MASKED>(s_col, a, places, last_mask);
+        hist_count_vec<KeyT, MASKED>(s_col, b, places, last_mask);
+        hist_count_vec<KeyT, MASKED>(s_col, c, places, last_mask);
+        hist_count_vec<KeyT, MASKED>(s_col, d, places, last_mask);
     }
     for (; i < nvec; i += stride) {
         uint4 a = __ldcs(vp + i);
         if (enc) a = hist_encode_vec<KeyT>(a, codec);
-        hist_count_vec<KeyT>(s_col, a);
+        hist_count_vec<KeyT, MASKED>(s_col, a, places, last_mask);
     }
     // ragged tail (n not a multiple of the vector width)
     if (blockIdx.x == 0) {
@@ -111,8 +119,11 @@ global_histogram_kernel(const KeyT* __restrict__ keys, uint64_t n, unsigned long
             KeyT k = keys[t];
             if (enc) k = codec_encode<KeyT>(k, static_cast<KeyT>(codec.a), static_cast<KeyT>(codec.b), static_cast<KeyT>(codec.d));
 #pragma unroll
-            for (int p = 0; p < PLACES; ++p)
-                atomicAdd(&s_col[(p * kRadix + (static_cast<uint32_t>(k >> (8 * p)) & 255u)) * COLS], 1u);
+            for (int p = 0; p < PLACES; ++p) {
+                if (MASKED && p >= places) break;
+                const uint32_t m = (MASKED && p == places - 1) ? last_mask : 255u;
+                atomicAdd(&s_col[(p * kRadix + (static_cast<uint32_t>(k >> (8 * p)) & m)) * COLS], 1u);
+            }
         }
     }
     __syncthreads();
@@ -276,10 +287,23 @@ cudaError_t launch_global_histogram_bits(const void* keys, uint64_t n, int key_b
                                          uint32_t last_bits)
 {
     const KeyCodec codec = codec_in ? *codec_in : KeyCodec();
+    const uint32_t last_mask = (1u << last_bits) - 1u;
+    if (begin_bit == 0) {  // byte-aligned places: the fast kernel slices the loaded words, the last place keeps last_bits
+        const uint64_t vecs = n / (16 / key_bytes);
+        uint64_t w2 = (vecs + kHistThreads - 1) / kHistThreads;
+        if (w2 < 1) w2 = 1;
+        const unsigned g2 = static_cast<unsigned>(w2 < static_cast<uint64_t>(sm_count) ? w2 : sm_count);
+        if (key_bytes == 4)
+            global_histogram_kernel<uint32_t, true><<<g2, kHistThreads, hist_smem_bytes<uint32_t>(), stream>>>(
+                static_cast<const uint32_t*>(keys), n, ghist, codec, places, last_mask);
+        else
+            global_histogram_kernel<uint64_t, true><<<g2, kHistThreads, hist_smem_bytes<uint64_t>(), stream>>>(
+                static_cast<const uint64_t*>(keys), n, ghist, codec, places, last_mask);
+        return cudaGetLastError();
+    }
     uint64_t want = (n + kHistThreads * 4 - 1) / (kHistThreads * 4);
     if (want < 1) want = 1;
     const unsigned grid = static_cast<unsigned>(want < static_cast<uint64_t>(sm_count) ? want : sm_count);
-    const uint32_t last_mask = (1u << last_bits) - 1u;
     if (key_bytes == 4)
         global_histogram_bits_kernel<uint32_t><<<grid, kHistThreads, hist_smem_bytes<uint32_t>(), stream>>>(
             static_cast<const uint32_t*>(keys), n, ghist, codec, begin_bit, places, last_mask);
@@ -1658,6 +1682,10 @@ cudaError_t configure_kernels()
     if ((e = cudaFuncSetAttribute(global_histogram_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(hist_smem_bytes<uint32_t>()))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(global_histogram_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(hist_smem_bytes<uint64_t>()))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(global_histogram_kernel<uint32_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(hist_smem_bytes<uint32_t>()))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(global_histogram_kernel<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(hist_smem_bytes<uint64_t>()))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(global_histogram_bits_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(hist_smem_bytes<uint32_t>()))) != cudaSuccess) return e;

@@ -364,11 +364,11 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
     }
     OSB_TRY(cudaEventRecord(h->ev[2], q));
 
-    // 5. local OneSweep.  After a coarse exchange every key of this rank has the same top log2(R) bits: the local sort
-    //    runs on the bits below them only (its last digit is 8 - log2(R) bits wide: fewer bins, longer runs), and any
-    //    digit on which the received keys happen to agree is skipped on the device.
-    st = coarse ? osb200_sort_bits(h->local, h->recv_buf, nullptr, mine, 0, static_cast<int>(xshift), q)
-                : osb200_sort_keys_u32(h->local, h->recv_buf, mine, q);
+    // 5. local OneSweep over the whole key.  (After a coarse exchange the keys of a rank share their top log2(R) bits, and a
+    //    sort on the bits below them alone -- osb200_sort_bits(0, 32 - log2 R) -- is correct too, but measured slower at 2^30
+    //    keys: 12.6 ms against 11.1 ms, its masked histogram costs 1.35 instead of 0.73 ms and its 5-bit last digit takes
+    //    the few-bins scatter, 3.44 instead of 2.59 ms; profiles/r02_sharded_local_sort_bits.txt.)
+    st = osb200_sort_keys_u32(h->local, h->recv_buf, mine, q);
     if (st != OSB200_OK) return st;
     OSB_TRY(cudaEventRecord(h->ev[3], q));
     *d_out = h->recv_buf;
