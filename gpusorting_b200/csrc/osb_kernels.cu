@@ -833,6 +833,11 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     static_assert(T < 32768, "agg16 holds 15-bit counts");
     extern __shared__ __align__(128) unsigned char s_raw[];
     S& sm = *reinterpret_cast<S*>(s_raw);
+    // pairs: key and payload of a tile slot are ONE 64-bit word of shared memory ({key, payload}; `sorted` and `sorted_val`
+    // are adjacent and together hold T such words) -- one transposing STS.64 and one LDS.64 per pair instead of two of each,
+    // and the payload's destination is the key's plus a constant (reference: OneSweep.cu:522-599 moves them separately)
+    static_assert(!PAIRS || (sizeof(KeyT) == 4 && offsetof(S, sorted_val) == offsetof(S, sorted) + sizeof(KeyT) * T), "kv layout");
+    uint2* const kv = reinterpret_cast<uint2*>(sm.sorted);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt = lanemask_lt();
@@ -1031,8 +1036,8 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift, dmask), lt);
-        sm.sorted[slot] = key[i];
-        if constexpr (PAIRS) sm.sorted_val[slot] = val[i];
+        if constexpr (PAIRS) kv[slot] = make_uint2(static_cast<uint32_t>(key[i]), val[i]);
+        else sm.sorted[slot] = key[i];
     }
 #endif
 
@@ -1051,6 +1056,14 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     // (profiles/r01_p2p_store_ub.txt: 128-B aligned 680-716 GB/s vs 390-580 GB/s at 4-byte alignment).
     const bool dec = (sm.plan_bits >> 1) & kCodecDecodeOnStore;
     const KeyT ca = static_cast<KeyT>(codec.a), cb = static_cast<KeyT>(codec.b), cd = static_cast<KeyT>(codec.d);
+    // pairs: a payload goes where its key goes, in the other output array (same element size: a constant byte distance)
+    long long val_delta = 0;
+    if constexpr (PAIRS) {
+        const bool swap = sm.plan_bits & 1u;
+        val_delta = reinterpret_cast<const char*>(swap ? val0 : val1) - reinterpret_cast<const char*>(swap ? buf0 : buf1);
+    }
+    auto slot_key = [&](uint32_t x) -> KeyT { if constexpr (PAIRS) return static_cast<KeyT>(kv[x].x); else return sm.sorted[x]; };
+    (void)slot_key;
     if (pp.dbits <= 5) {
         const uint32_t nbins = 1u << pp.dbits;
         for (uint32_t b = 0; b < nbins; ++b) {
@@ -1064,10 +1077,18 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
             for (uint32_t p = tid; p < total; p += THREADS) {
                 if (p >= ga) {
                     const uint32_t x = lo + p - ga;
-                    KeyT k = sm.sorted[x];
-                    if (dec) k = codec_decode<KeyT>(k, ca, cb, cd);
-                    st_stream(reinterpret_cast<KeyT*>(kp) + x, k);
-                    if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[b]) + x, sm.sorted_val[x]);
+                    if constexpr (PAIRS) {
+                        const uint2 e = kv[x];
+                        KeyT k = static_cast<KeyT>(e.x);
+                        if (dec) k = codec_decode<KeyT>(k, ca, cb, cd);
+                        KeyT* dst = reinterpret_cast<KeyT*>(kp) + x;
+                        st_stream(dst, k);
+                        st_stream(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(dst) + val_delta), e.y);
+                    } else {
+                        KeyT k = sm.sorted[x];
+                        if (dec) k = codec_decode<KeyT>(k, ca, cb, cd);
+                        st_stream(reinterpret_cast<KeyT*>(kp) + x, k);
+                    }
                 }
             }
         }
@@ -1079,15 +1100,21 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;
-            const KeyT k = sm.sorted[idx];
-            const uint32_t d = digit_of(k, shift, dmask);
+            if constexpr (PAIRS) {
+                const uint2 e = kv[idx];
+                KeyT* dst = reinterpret_cast<KeyT*>(sm.keyptr[digit_of(static_cast<KeyT>(e.x), shift, dmask)]) + idx;
+                st_stream(dst, static_cast<KeyT>(e.x));
+                st_stream(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(dst) + val_delta), e.y);
+            } else {
+                const KeyT k = sm.sorted[idx];
+                const uint32_t d = digit_of(k, shift, dmask);
 #if OSB_ABL & 2
-            KeyT* dst = reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx;
-            asm volatile("" ::"l"(dst), "l"(static_cast<unsigned long long>(k)));  // pointer math and LDS stay, the store does not
+                KeyT* dst = reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx;
+                asm volatile("" ::"l"(dst), "l"(static_cast<unsigned long long>(k)));  // pointer math and LDS stay, the store does not
 #else
-            st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
+                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, k);
 #endif
-            if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
+            }
         }
 #endif
     } else {  // ragged last tile, or the last pass of a typed sort (keys leave decoded)
@@ -1095,10 +1122,17 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
         for (int j = 0; j < K; ++j) {
             const uint32_t idx = j * THREADS + tid;
             if (idx < valid) {
-                const KeyT k = sm.sorted[idx];
-                const uint32_t d = digit_of(k, shift, dmask);
-                st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, dec ? codec_decode<KeyT>(k, ca, cb, cd) : k);
-                if constexpr (PAIRS) st_stream(reinterpret_cast<uint32_t*>(sm.valptr[d]) + idx, sm.sorted_val[idx]);
+                if constexpr (PAIRS) {
+                    const uint2 e = kv[idx];
+                    const KeyT k = static_cast<KeyT>(e.x);
+                    KeyT* dst = reinterpret_cast<KeyT*>(sm.keyptr[digit_of(k, shift, dmask)]) + idx;
+                    st_stream(dst, dec ? codec_decode<KeyT>(k, ca, cb, cd) : k);
+                    st_stream(reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(dst) + val_delta), e.y);
+                } else {
+                    const KeyT k = sm.sorted[idx];
+                    const uint32_t d = digit_of(k, shift, dmask);
+                    st_stream(reinterpret_cast<KeyT*>(sm.keyptr[d]) + idx, dec ? codec_decode<KeyT>(k, ca, cb, cd) : k);
+                }
             }
         }
     }
@@ -1119,8 +1153,11 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
 // loads fly during the chained scan and the key scatter), go through the SAME 64 KB buffer at the remembered slots, and
 // are scattered with the digit the key scatter has noted per slot (one byte).  100 KB of shared memory, two CTAs per SM.
 // =====================================================================================================
+// Round 2, n = 2^30 pairs, ms per pass: this kernel 5.30; the PAIRS instantiation of digit_binning_wide_kernel (8,192-pair
+// tiles, key and payload staged as one 64-bit word) 5.07 -> that one is the default (profiles/r02_pairs_u64_sweep.txt);
+// -DOSB_PAIRS16K=1 selects this kernel.
 #ifndef OSB_PAIRS16K
-#define OSB_PAIRS16K 1
+#define OSB_PAIRS16K 0
 #endif
 template <int WARPS, int K>
 struct PairsSmem {
@@ -1374,8 +1411,11 @@ struct RingSmem {
 #ifndef OSB_STEP
 #define OSB_STEP 8
 #endif
-#ifndef OSB_PAIRS_LOOK  // the pairs kernel looks back with its 32 keys still in registers: a narrower window
+#ifndef OSB_PAIRS_LOOK  // (key, payload) pairs, either kernel
 #define OSB_PAIRS_LOOK 16
+#endif
+#ifndef OSB_U64_LOOK    // 64-bit keys: 8,192-key tiles, twice the tiles per byte
+#define OSB_U64_LOOK 32
 #endif
 #ifndef OSB_RING_K  // u32 geometry of the ring kernel, overridable for sweeps: keys per thread, resident CTAs per SM
 #define OSB_RING_K 16
@@ -1551,11 +1591,11 @@ template <typename KeyT, bool PAIRS> struct WideGeom;
 #define OSB_WIDE_MINB 2
 #endif
 template <> struct WideGeom<uint32_t, false> { static constexpr int K = OSB_WIDE_K, WARPS = OSB_WIDE_WARPS, MINB = OSB_WIDE_MINB, LOOK = OSB_LOOK, STEP = OSB_STEP; };
-template <> struct WideGeom<uint32_t, true>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
+template <> struct WideGeom<uint32_t, true>  { static constexpr int K = 16, WARPS = 16, MINB = 2, LOOK = OSB_PAIRS_LOOK, STEP = OSB_STEP; };
 #ifndef OSB_U64_K
 #define OSB_U64_K 16
 #endif
-template <> struct WideGeom<uint64_t, false> { static constexpr int K = OSB_U64_K, WARPS = 16, MINB = 2, LOOK = OSB_LOOK, STEP = OSB_STEP; };
+template <> struct WideGeom<uint64_t, false> { static constexpr int K = OSB_U64_K, WARPS = 16, MINB = 2, LOOK = OSB_U64_LOOK, STEP = OSB_STEP; };
 
 template <typename KeyT, bool PAIRS, int RANK_MODE>
 static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t* in_val, uint32_t* out_val, uint64_t n,
