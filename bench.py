@@ -89,6 +89,12 @@ def ncu_traffic_bytes():
     return None
 
 
+# NVML queries take driver locks that CUDA API calls of the same process also need, and the sampling thread competes for the
+# GIL: at 2 ms per sample the sharded loop (which has a host sync per step) lost ~5 ms per step on the sampled rank
+# (profiles/r02_bench_n2_sampler_2ms.json).  20 ms still gives >= 10 samples inside the shortest timed region.
+CLOCK_SAMPLE_S = float(os.environ.get("OSB_CLOCK_SAMPLE_MS", "20")) / 1e3
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons through NVML while the timed region runs."""
 
@@ -125,7 +131,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(CLOCK_SAMPLE_S)
 
     def result(self):
         self.stop_flag = True
@@ -323,7 +329,7 @@ def main():
             "clocks": result["clocks"],
             "verified": result["verified"],
         }
-        for k in ("extra_configs", "ref_cuda", "entropy_sweep", "phases_ms"):
+        for k in ("extra_configs", "ref_cuda", "entropy_sweep", "phases_ms", "per_rank"):
             if k in result:
                 line[k] = result[k]
         if world == 1 and not args.no_cpu_baseline:

@@ -228,6 +228,12 @@ def bench_sharded(args, rank: int, world: int, local_rank: int, n: int):
     verified = (verify_global_order(res, rank, world) and int(total_out) == int(total_in)
                 and global_multiset_checksum(res) == checksum_in)
     ph = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
+    # every rank's own view (phases are measured by the rank's own CUDA events; a rank that arrives early at a collective
+    # waits inside the phase that contains it)
+    mine = torch.tensor([ms] + [ph[k] for k in sorted(ph)], dtype=torch.float64, device="cuda")
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    per_rank = [dict(zip(["ms_per_step"] + sorted(ph), (round(float(x), 4) for x in v))) for v in allv]
 
     # end to end: pinned host keys in, sorted slice back out
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
@@ -251,7 +257,7 @@ def bench_sharded(args, rank: int, world: int, local_rank: int, n: int):
     # kernels launched per sharded sort: MSD histogram + exchange pass (+ its scan in staged mode) + the local sort's
     launches_per_sort = 1 + 1 + s.local_info("launches_per_sort")
     result = {
-        "ms_per_step": ms, "pass_ms": local_pass_ms, "kernel_ms": ph, "phases_ms": ph,
+        "ms_per_step": ms, "pass_ms": local_pass_ms, "kernel_ms": ph, "phases_ms": ph, "per_rank": per_rank,
         "kernel": "digit_binning_wide_kernel (local sort) + fused NVLink exchange pass",
         "variant": s.local_info("variant"), "tile_keys": s.local_info("tile_keys"),
         "rank_mode": "atomic" if s.local_info("rank_mode") == 0 else "ballot", "e2e_ms_per_step": e2e_ms, "e2e_steps": e2e_steps,
