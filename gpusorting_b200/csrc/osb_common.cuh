@@ -97,8 +97,9 @@ template <typename KeyT> __device__ __forceinline__ uint32_t digit_of(KeyT k, ui
 // launches and never synchronises, yet passes whose digit is the same for ALL keys (one non-empty bin in the global
 // histogram) move nothing.  Reference idea: the entropy benchmark of GPUSortingD3D12/Tests.h:383-393 shows what low-entropy
 // inputs cost; skipping is this repository's answer (the reference itself always runs its 4 passes).
+constexpr uint32_t kPlanHotShift = 16;  // SortPlan::skip_mask bit 16+p: pass p is "hot" (a bin holds >= n/8 keys: HOT instantiation)
 struct SortPlan {
-    uint32_t skip_mask;   // bit p: pass p is skipped (its CTAs exit at once)
+    uint32_t skip_mask;   // bit p: pass p is skipped (its CTAs exit at once); bits 16+p: hot passes
     uint32_t executed;    // number of passes that run; odd -> the result is in the alt buffers -> copy_back_kernel moves it
     uint32_t first_exec;  // first / last executed pass (typed keys: encode in the first one, decode in the last one)
     uint32_t last_exec;

@@ -55,6 +55,7 @@ struct osb200_sorter {
     bool atomic_order_ok = false;
     bool short_circuit = true;   // skip passes whose digit is the same for all keys (decided on the device, no host sync)
     bool small_path = true;      // n <= one tile: the single-CTA shared-memory sort (one launch)
+    bool hot_passes = true;      // low-entropy digit places run in the HOT instantiation of the pass (decided on the device)
 
     void* alt_keys = nullptr;
     uint32_t* alt_vals = nullptr;
@@ -173,7 +174,9 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
         OSB_TRY(osb::launch_global_histogram_bits(d_keys, n, s->key_bytes, s->ghist(), s->sm_count, stream, codec ? &enc : nullptr,
                                                   static_cast<uint32_t>(begin_bit), places, last_bits));
     OSB_TRY(mark());
-    OSB_TRY(osb::launch_scan(s->ghist(), s->gbase(), places, stream, use_plan ? s->plan() : nullptr, n, s->short_circuit));
+    // hot passes (low-entropy inputs): the default kernel has a second instantiation for them; both are enqueued per pass
+    const bool hot_passes = use_plan && s->hot_passes && !(d_vals && osb::binning_tile_keys(4, true, s->cfg) == 16384);
+    OSB_TRY(osb::launch_scan(s->ghist(), s->gbase(), places, stream, use_plan ? s->plan() : nullptr, n, s->short_circuit, hot_passes));
     OSB_TRY(mark());
 
     void* src = d_keys;
@@ -188,6 +191,7 @@ int sort_impl(osb200_sorter* s, void* d_keys, uint32_t* d_vals, uint64_t n, cuda
         cfg.digit_bits = p == places - 1 ? last_bits : 8u;
         cfg.place = static_cast<uint32_t>(p);
         if (use_plan) cfg.plan = s->plan();
+        cfg.hot_passes = hot_passes;
         if (codec) {
             cfg.codec = *codec;
             cfg.codec.flags = use_plan ? osb::kCodecFromPlan
@@ -553,6 +557,7 @@ int osb200_set_option(osb200_handle h, const char* key, int64_t value)
     if (!std::strcmp(key, "profile")) { h->profile = value != 0; return OSB200_OK; }
     if (!std::strcmp(key, "short_circuit")) { h->short_circuit = value != 0; return OSB200_OK; }
     if (!std::strcmp(key, "small_path")) { h->small_path = value != 0; return OSB200_OK; }
+    if (!std::strcmp(key, "hot_passes")) { h->hot_passes = value != 0; return OSB200_OK; }
     if (!std::strcmp(key, "spin_cap")) {
         if (value < 1 || value > (1ll << 30)) return OSB200_ERR_INVALID_ARG;
         h->cfg.spin_cap = static_cast<uint32_t>(value);
@@ -586,19 +591,26 @@ int64_t osb200_get_info(osb200_handle h, const char* key)
     if (check_handle(h) != OSB200_OK || !key) return OSB200_ERR_INVALID_ARG;
     if (!std::strcmp(key, "tile_keys")) return osb::binning_tile_keys(h->key_bytes, h->value_bytes != 0, h->cfg);
     if (!std::strcmp(key, "launches_per_sort")) {  // histogram + scan + one pass per place (+ copy-back: keys [+ values])
-        const bool cb = h->cfg.variant == osb::kVariantWide && h->short_circuit;
-        return 2 + h->key_bytes + (cb ? (h->value_bytes ? 2 : 1) : 0);
+        const bool wide = h->cfg.variant == osb::kVariantWide;
+        const bool cb = wide && h->short_circuit;
+        return 2 + h->key_bytes * ((wide && h->hot_passes) ? 2 : 1) + (cb ? (h->value_bytes ? 2 : 1) : 0);
     }
     if (!std::strcmp(key, "memsets_per_sort")) return h->cfg.variant != osb::kVariantTilePerCta ? 2 : 1;
     if (!std::strcmp(key, "short_circuit")) return h->short_circuit ? 1 : 0;
     if (!std::strcmp(key, "small_path")) return h->small_path ? 1 : 0;
+    if (!std::strcmp(key, "hot_passes")) return h->hot_passes ? 1 : 0;
+    if (!std::strcmp(key, "last_hot_mask")) {
+        osb::SortPlan pl;
+        if (cudaMemcpy(&pl, h->plan(), sizeof(pl), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+        return static_cast<int>((pl.skip_mask >> osb::kPlanHotShift) & 0xffu);
+    }
     if (!std::strcmp(key, "small_path_max_n")) return osb::segment_sort_capacity(h->key_bytes, false);
     if (!std::strcmp(key, "spin_cap")) return h->cfg.spin_cap;
     if (!std::strcmp(key, "last_skip_mask") || !std::strcmp(key, "last_executed_passes")) {
         // the plan of the last sort on this handle (synchronises the device: introspection / tests only)
         osb::SortPlan pl;
         if (cudaMemcpy(&pl, h->plan(), sizeof(pl), cudaMemcpyDeviceToHost) != cudaSuccess) return OSB200_ERR_CUDA;
-        return key[5] == 's' ? static_cast<int64_t>(pl.skip_mask) : static_cast<int64_t>(pl.executed);
+        return key[5] == 's' ? static_cast<int64_t>(pl.skip_mask & 0xffffu) : static_cast<int64_t>(pl.executed);
     }
     if (!std::strcmp(key, "sm_count")) return h->sm_count;
     if (!std::strcmp(key, "rank_mode")) return h->cfg.rank_mode;

@@ -207,7 +207,7 @@ cudaError_t launch_digit_histogram(const void* keys, uint64_t n, int key_bytes, 
 // =====================================================================================================
 __global__ void __launch_bounds__(kRadix)
 scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ gbase, int places,
-            SortPlan* plan, unsigned long long n, int allow_skip)
+            SortPlan* plan, unsigned long long n, int allow_skip, int allow_hot)
 {
     __shared__ unsigned long long s_warp[kRadix / 32];
     const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
@@ -222,10 +222,13 @@ scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __
         }
         if (lane == 31) s_warp[warp] = incl;
         const int single_bin = __syncthreads_or(plan != nullptr && allow_skip && c == n);
+        // hot pass: one bin holds at least an eighth of the keys (and the input is large enough for resident CTAs to pay)
+        const int hot_bin = __syncthreads_or(plan != nullptr && allow_hot && n >= (1ull << 22) && c * 8ull >= n);
         unsigned long long pre = 0;
         for (int w = 0; w < warp; ++w) pre += s_warp[w];
         gbase[p * kRadix + d] = pre + incl - c;
         if (single_bin) skip_mask |= 1u << p;
+        else if (hot_bin) skip_mask |= 1u << (kPlanHotShift + p);
         __syncthreads();  // s_warp is reused by the next place
     }
     if (plan != nullptr && d == 0) {
@@ -240,9 +243,9 @@ scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __
 }
 
 cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream,
-                        SortPlan* plan, uint64_t n, bool allow_skip)
+                        SortPlan* plan, uint64_t n, bool allow_skip, bool allow_hot)
 {
-    scan_kernel<<<1, kRadix, 0, stream>>>(ghist, gbase, places, plan, n, allow_skip ? 1 : 0);
+    scan_kernel<<<1, kRadix, 0, stream>>>(ghist, gbase, places, plan, n, allow_skip ? 1 : 0, allow_hot ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -794,6 +797,40 @@ lookback_wide(uint16_t* agg16, const uint64_t* incl64, uint32_t tile, uint32_t d
     }
 }
 
+
+// ---- hot digit -------------------------------------------------------------------------------------------------------
+// Low-entropy inputs (the reference's entropy presets 2-5, UtilityKernels.cuh:42-52: AND of several random words) put a
+// large share of every tile into ONE bin.  Same-address returning atomics serialise lane by lane, so such passes ran at
+// half the uniform rate (54 Gkeys/s at preset 5 against 97 uniform).  Remedy: the Scan kernel flags a digit place whose
+// global histogram has a bin with >= n/8 keys ("hot pass", SortPlan); such a pass is executed by the HOT instantiation of
+// digit_binning_wide_kernel -- resident CTAs striding over the tiles -- in which the keys of a tile's most frequent digit
+// are ranked with one ballot per round (rank = popc of the lower lanes + a running count in a register) and only the other
+// lanes issue the atomic; the hot keys' slots are consecutive, so their transposing stores are conflict-free as well.
+// It is a second instantiation rather than a branch because the extra state costs registers the spill-free plain loop does
+// not have (the attempt to keep both in one kernel spilled 150 bytes in the uniform path); the host enqueues both kernels
+// for every pass and the plan decides which one returns at once -- the resident form makes the idle one a ~5 us launch.
+constexpr uint32_t kNoHotDigit = 0xffffffffu;
+#ifndef OSB_HOT_MINB  // resident CTAs per SM of the HOT instantiation: 1 = up to 128 registers, no spills (profiles/r02_hot_passes.txt)
+#define OSB_HOT_MINB 1
+#endif
+
+__device__ __forceinline__ void hot_digit_publish(uint32_t tile_count, uint32_t* s_wmax)
+{
+    const int tid = threadIdx.x;
+    if (tid < kRadix) {
+        const uint32_t m = __reduce_max_sync(0xffffffffu, (tile_count << 8) | static_cast<uint32_t>(tid));
+        if ((tid & 31) == 0) s_wmax[tid >> 5] = m;
+    }
+}
+__device__ __forceinline__ uint32_t hot_digit_of_tile(const uint32_t* s_wmax, uint32_t tile_keys)
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < kRadix / 32; ++w) m = max(m, s_wmax[w]);
+    m = __shfl_sync(0xffffffffu, m, 0);
+    return (m >> 8) >= tile_keys / 8 ? (m & 255u) : kNoHotDigit;
+}
+
 // Per-launch parameters of one DigitBinningPass.
 struct PassParams {
     uint32_t shift;        // bit position of this pass's digit
@@ -816,13 +853,14 @@ struct WideSmem {
     unsigned long long valptr[PAIRS ? kRadix : 1];
     uint32_t run[32];                                // few-bins passes: first slot (low 16 bits) | live length (high 16)
     uint32_t wtot[kRadix / 32];
+    uint32_t wmax[kRadix / 32];                      // (HOT) per digit warp: max of (tile count << 8 | digit)
     uint32_t tile;                                   // this CTA's tile, 0xffffffff = the plan skips this pass
     uint32_t plan_bits;                              // bit 0: source is the alt buffer; bits 1-2: codec flags of this pass
     alignas(8) uint64_t bar;                         // (TMA tile load) "tile landed" mbarrier
 };
 
-template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP, int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB)
+template <typename KeyT, bool PAIRS, int K, int WARPS, int RANK_MODE, int LOOK, int STEP, int MINB, bool HOT = false>
+__global__ void __launch_bounds__(WARPS * 32, HOT ? OSB_HOT_MINB : MINB)
 digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1, uint64_t n,
                           const unsigned long long* __restrict__ gbase, uint16_t* agg16, uint64_t* incl64,
                           uint32_t* ticket, PassParams pp, KeyCodec codec)
@@ -858,22 +896,31 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     // after spin_cap polls (rereduce_tile), so the chained scan cannot hang.  Every thread reads the 16-byte plan itself (L1 hit
     // for all but the first CTA of an SM).
     uint32_t my_bits = (codec.flags & (kCodecEncodeOnLoad | kCodecDecodeOnStore)) << 1;
-    bool my_skip = false;
+    bool my_skip = false, my_hot = false;
     if (pp.plan != nullptr) {
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(pp.plan));
         SortPlan pl; pl.skip_mask = raw.x; pl.executed = raw.y; pl.first_exec = raw.z; pl.last_exec = raw.w;
         my_skip = (pl.skip_mask >> pp.place) & 1u;
+        my_hot = (pl.skip_mask >> (kPlanHotShift + pp.place)) & 1u;
         my_bits = plan_src_is_alt(pl, pp.place) ? 1u : 0u;
         if (codec.flags & kCodecFromPlan)
             my_bits |= (pp.place == pl.first_exec ? kCodecEncodeOnLoad << 1 : 0u) | (pp.place == pl.last_exec ? kCodecDecodeOnStore << 1 : 0u);
     }
     if (my_skip) return;
+    if (HOT != my_hot) return;  // a pass is executed by exactly one of the two instantiations the host enqueues
+    const uint32_t num_tiles = static_cast<uint32_t>((n + T - 1) / T);
+    // plain: one tile per CTA (the loop body runs once); HOT: resident CTAs stride over the tiles
+    for (uint32_t tile = blockIdx.x; HOT ? tile < num_tiles : tile == blockIdx.x; tile += HOT ? gridDim.x : 0x40000000u) {
+    if (HOT && tile != blockIdx.x) {  // (the barrier at the end of the previous tile separates this from its last reads)
+        uint4* h4 = reinterpret_cast<uint4*>(sm.hist);
+        for (int i = tid; i < WARPS * kRadix / 4; i += THREADS) h4[i] = make_uint4(0, 0, 0, 0);
+    }
     if (tid == 0) {
         sm.plan_bits = my_bits;
-        sm.tile = blockIdx.x;
+        sm.tile = tile;
     }
-    const uint32_t tile = blockIdx.x;
 #else
+    static_assert(!HOT, "the HOT instantiation is written for the ticket-less path");
     if (tid == 0) {
         // The device plan (if any) decides whether this pass runs at all, which buffer it reads, and -- typed keys --
         // whether it is the pass that encodes / decodes.  Without a plan the launch arguments are taken as they are.
@@ -985,6 +1032,7 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
         if (pp.stall_every == 0 || (tile % pp.stall_every) != pp.stall_every - 1)
             st_relaxed_gpu_u16(agg16 + agg_index(tile, tid), kAggReady | tile_count);
     }
+    if constexpr (HOT) hot_digit_publish(tile_count, sm.wmax);
     tile_excl = block_excl_scan_256<THREADS>(tile_count, sm.wtot);
     if (tid < kRadix) {
         uint32_t run = tile_excl;
@@ -1033,11 +1081,28 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
 #pragma unroll
     for (int i = 0; i < K; ++i) asm volatile("" ::"l"(static_cast<unsigned long long>(key[i])));  // keep the loads live
 #else
+    uint32_t hot = kNoHotDigit;
+    if constexpr (HOT && RANK_MODE == kRankAtomic) hot = hot_digit_of_tile(sm.wmax, T);
+    if (HOT && hot != kNoHotDigit) {
+        uint32_t hot_run = __shfl_sync(0xffffffffu, wh[hot], 0);  // this warp's next slot of the hot digit (warp-uniform)
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-        const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift, dmask), lt);
-        if constexpr (PAIRS) kv[slot] = make_uint2(static_cast<uint32_t>(key[i]), val[i]);
-        else sm.sorted[slot] = key[i];
+        for (int i = 0; i < K; ++i) {
+            const uint32_t d = digit_of(key[i], shift, dmask);
+            const bool is_hot = d == hot;
+            const uint32_t b = __ballot_sync(0xffffffffu, is_hot);
+            uint32_t slot = hot_run + __popc(b & lt);
+            if (!is_hot) slot = warp_rank_and_count<RANK_MODE>(wh, d, lt);
+            hot_run += __popc(b);
+            if constexpr (PAIRS) kv[slot] = make_uint2(static_cast<uint32_t>(key[i]), val[i]);
+            else sm.sorted[slot] = key[i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const uint32_t slot = warp_rank_and_count<RANK_MODE>(wh, digit_of(key[i], shift, dmask), lt);
+            if constexpr (PAIRS) kv[slot] = make_uint2(static_cast<uint32_t>(key[i]), val[i]);
+            else sm.sorted[slot] = key[i];
+        }
     }
 #endif
 
@@ -1139,6 +1204,10 @@ digit_binning_wide_kernel(KeyT* buf0, KeyT* buf1, uint32_t* val0, uint32_t* val1
     OSB_PHASE(6);
 #if OSB_EXP & 32
     if (tid == 0) atomicAdd(&g_phase[7], 1ull);
+#endif
+#if !OSB_TICKET
+    if constexpr (HOT) __syncthreads();  // the next tile's histogram clear and staging must not overtake this tile's readers
+    }  // tile loop
 #endif
 }
 
@@ -1618,6 +1687,26 @@ static cudaError_t launch_wide_variant(const void* in, void* out, const uint32_t
     kern<<<static_cast<unsigned>(tiles), S::THREADS, sizeof(S), stream>>>(
         static_cast<KeyT*>(const_cast<void*>(in)), static_cast<KeyT*>(out), const_cast<uint32_t*>(in_val), out_val, n, gbase,
         agg16, incl64, ticket, pp, cfg.codec);
+#if !OSB_TICKET
+    if (cfg.plan != nullptr && cfg.hot_passes) {
+        // the HOT instantiation of the same pass: resident CTAs; returns at once unless the plan calls the pass hot
+        // (same geometry, one resident CTA per SM with up to 128 registers: no spills.  Measured alternatives,
+        // profiles/r02_hot_passes.txt: two CTAs per SM at 64 registers spill 280 bytes and lose; 1,024 threads x 16 keys
+        // at 64 registers is 4-5 % slower than this)
+        using SH = S;
+        auto hot = digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, true>;
+        static int per_sm = 0;  // (one value per instantiation of this function template)
+        if (per_sm == 0) {
+            int b = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, hot, SH::THREADS, sizeof(SH)) != cudaSuccess || b < 1) b = 1;
+            per_sm = b;
+        }
+        const uint64_t cap = static_cast<uint64_t>(cfg.sm_count) * per_sm;
+        hot<<<static_cast<unsigned>(tiles < cap ? tiles : cap), SH::THREADS, sizeof(SH), stream>>>(
+            static_cast<KeyT*>(const_cast<void*>(in)), static_cast<KeyT*>(out), const_cast<uint32_t*>(in_val), out_val, n, gbase,
+            agg16, incl64, ticket, pp, cfg.codec);
+    }
+#endif
     return cudaGetLastError();
 }
 
@@ -1658,8 +1747,14 @@ static cudaError_t set_wide_attr()
 {
     using G = WideGeom<KeyT, PAIRS>;
     using S = WideSmem<KeyT, PAIRS, G::K, G::WARPS>;
-    return cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+    cudaError_t e = cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+#if !OSB_TICKET
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(digit_binning_wide_kernel<KeyT, PAIRS, G::K, G::WARPS, RANK_MODE, G::LOOK, G::STEP, G::MINB, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(S)));
+#endif
+    return e;
 }
 
 // ---- variant-0 geometry ------------------------------------------------------------------------------

@@ -30,6 +30,7 @@ struct BinningConfig {
     uint32_t place = 0;               // index of this pass in the plan
     uint32_t spin_cap = 2048;         // lookback polls of one predecessor before the digit thread re-reduces that tile itself
     uint32_t debug_stall_every = 0;   // test hook: tiles with tile % N == N-1 never publish their reduction (0 = off)
+    bool hot_passes = false;          // also enqueue the HOT instantiation (the plan decides which of the two runs the pass)
 };
 
 // keys per partition tile for a key width / pairs flag / variant (host needs it to size descriptors)
@@ -51,7 +52,7 @@ cudaError_t launch_digit_histogram(const void* keys, uint64_t n, int key_bytes, 
 // With plan != null the kernel also writes the device launch plan: a place is skipped when one of its bins holds all n
 // keys (allow_skip), and the first/last executed places are recorded for the typed-key codec.
 cudaError_t launch_scan(const unsigned long long* ghist, unsigned long long* gbase, int places, cudaStream_t stream,
-                        SortPlan* plan = nullptr, uint64_t n = 0, bool allow_skip = false);
+                        SortPlan* plan = nullptr, uint64_t n = 0, bool allow_skip = false, bool allow_hot = false);
 
 // GlobalHistogram of a begin_bit/end_bit sort: place p counts the digit (key >> (begin_bit + 8p)) & mask_p, mask_p = 255
 // except for the last place, which keeps last_bits bits.  (The byte-aligned full-width case uses launch_global_histogram.)

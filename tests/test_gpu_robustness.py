@@ -71,9 +71,13 @@ def test_short_circuit_can_be_switched_off(g, sorter, oracle):
     sorter.sort_keys(t)
     assert np.array_equal(host(t), np.sort(k))
     assert sorter.info("last_skip_mask") == 0 and sorter.info("last_executed_passes") == 4
+    # histogram + scan + per place the pass and its HOT twin (one of the two returns at once)
+    assert sorter.info("launches_per_sort") == 10
+    sorter.set_option("hot_passes", 0)
     assert sorter.info("launches_per_sort") == 6
+    sorter.set_option("hot_passes", 1)
     sorter.set_option("short_circuit", 1)
-    assert sorter.info("launches_per_sort") == 8  # + copy-back of keys and values (pairs-capable handle)
+    assert sorter.info("launches_per_sort") == 12  # + copy-back of keys and values (pairs-capable handle)
 
 
 @pytest.mark.parametrize("andc", [0, 1, 2, 3, 4])
@@ -188,3 +192,30 @@ def test_u64_fallback(g, oracle):
     s.sort_keys(t)
     assert np.array_equal(host(t, np.uint64), np.sort(k))
     s.close()
+
+
+@pytest.mark.parametrize("andc", [2, 3, 4])
+def test_hot_passes_low_entropy_keys_and_pairs(g, oracle, andc):
+    """Entropy presets 3-5 (UtilityKernels.cuh:42-52): one bin holds 34-78 % of every digit place, the Scan kernel flags
+    the passes hot and the HOT instantiation of the DigitBinningPass (one ballot per round for the tile's most frequent
+    digit) executes them; same results as the plain kernel and the oracle, stable for pairs."""
+    n = (1 << 22) + 4099
+    k = oracle.init_random_u32(n, andc, 5)
+    v = np.arange(n, dtype=np.uint32)
+    wk, wv = oracle.sort_pairs(k, v)
+    with g.OneSweepSorter(n, 4, 4) as s:
+        for hot in (1, 0):
+            s.set_option("hot_passes", hot)
+            t = dev(k)
+            s.sort_keys(t)
+            assert np.array_equal(host(t), wk)
+            assert (s.info("last_hot_mask") != 0) == bool(hot)
+            tk, tv = dev(k), dev(v)
+            s.sort_pairs(tk, tv)
+            assert np.array_equal(host(tk), wk) and np.array_equal(host(tv), wv)
+    with g.OneSweepSorter(n, 8, 0) as s8:  # 64-bit keys: the low word is low-entropy, the high word uniform
+        k8 = k.astype(np.uint64) | (oracle.init_random_u32(n, 0, 6).astype(np.uint64) << np.uint64(32))
+        t = dev(k8)
+        s8.sort_keys(t)
+        assert np.array_equal(host(t, np.uint64), np.sort(k8))
+        assert s8.info("last_hot_mask") & 0x0F == 0x0F and s8.info("last_hot_mask") & 0xF0 == 0
