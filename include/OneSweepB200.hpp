@@ -43,6 +43,14 @@ class OneSweepSorterB200 {
     {
         check(osb200_sort_keys_typed(h_, d_keys, n, key_type, descending ? 1 : 0, stream), "osb200_sort_keys_typed");
     }
+    // every segment [offsets[i], offsets[i+1]) sorted ascending and stable in place, one thread block per segment
+    // (reference: SplitSort, SegSort/SplitSort/SplitSort.cuh:702-938); d_values may be null; max_segment_len <= 16,384
+    void SegmentedSort(uint32_t* d_keys, uint32_t* d_values, const uint64_t* d_segment_offsets, uint64_t num_segments,
+                       uint32_t max_segment_len, void* stream = nullptr)
+    {
+        check(osb200_segmented_sort_u32(h_, d_keys, d_values, d_segment_offsets, num_segments, max_segment_len, stream),
+              "osb200_segmented_sort_u32");
+    }
     void SetOption(const char* key, int64_t value) { check(osb200_set_option(h_, key, value), "osb200_set_option"); }
     uint64_t Validate(const void* d_keys, uint64_t n, void* stream = nullptr)
     {

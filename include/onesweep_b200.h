@@ -159,6 +159,10 @@ OSB200_API int osb200_init_random_u32(uint32_t* d_keys, uint32_t* d_payload, uin
  *                    stability of every pass rests.  osb200_create verifies it on the device (a self-test kernel in the
  *                    production geometry) and falls back to 1 if it ever fails; 1 is the supported escape hatch: it uses
  *                    the reference's documented 8-ballot warp multisplit (Sort/OneSweep.cu:208-253) at ~2x the pass time.
+ *                    Round 2 saw the assumption fail in ONE development build of the pairs kernel (rank phase of some
+ *                    warps concurrent with the chained-scan loads of others, n >= 2^28; DESIGN.md 4.1,
+ *                    profiles/r02_pairs_order_violation.md); the shipped kernels never overlap the two and the GPU suite
+ *                    compares full-size sorts element by element.
  *   "variant"        kernel variant id (2 = default wide-tile kernel; 0/1 development baselines)
  *   "short_circuit"  1 (default) = digit passes on which ALL keys agree are skipped, decided on the device from the
  *                    global histogram without any host synchronisation; 0 = always run every pass like the reference
@@ -166,9 +170,16 @@ OSB200_API int osb200_init_random_u32(uint32_t* d_keys, uint32_t* d_payload, uin
  *                    tile itself (forward-progress fallback, reference: Sort/EmulatedDeadlocking.cu:159-267)
  *   "debug_stall_every"  test hook for that fallback: N > 0 makes every N-th tile withhold its reduction
  *   "profile"        1 = record CUDA events between the kernels of a sort (osb200_get_profile)
+ *   "small_path"     1 (default) = a sort of at most one tile (info "small_path_max_n": 16,384 keys, 8,192 for 64-bit keys)
+ *                    is ONE launch of the single-block shared-memory sort (see osb200_segmented_sort_u32); 0 = always the
+ *                    multi-kernel path
+ *   "hot_passes"     1 (default) = a digit place in which one bin holds >= n/8 keys (low-entropy inputs; reference presets
+ *                    UtilityKernels.cuh:42-52) is executed by the HOT instantiation of the DigitBinningPass, which ranks
+ *                    a tile's most frequent digit with one ballot per round instead of serialised same-address atomics;
+ *                    decided on the device, both instantiations are enqueued for every pass; 0 = plain kernel only
  * Info keys: "tile_keys","launches_per_sort","memsets_per_sort","sm_count","rank_mode","variant","atomic_order_ok",
- * "max_n","epoch","short_circuit","spin_cap","last_skip_mask","last_executed_passes" (the last two read the device plan
- * of the previous sort and synchronise). */
+ * "max_n","epoch","short_circuit","spin_cap","small_path","small_path_max_n","hot_passes","last_skip_mask",
+ * "last_hot_mask","last_executed_passes" (the last three read the device plan of the previous sort and synchronise). */
 OSB200_API int osb200_set_option(osb200_handle h, const char* key, int64_t value);
 OSB200_API int64_t osb200_get_info(osb200_handle h, const char* key);
 /* With option "profile"=1 every sort records CUDA events on its stream between its kernels.  Returns the number of
