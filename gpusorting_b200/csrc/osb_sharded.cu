@@ -14,12 +14,18 @@
 //                keys cross HBM once (read) + NVLink once (write);
 //        staged: DigitBinningPass into a local send buffer, then ncclSend/ncclRecv per peer (baseline).
 //   5. local OneSweep (osb200_sort_keys_u32) on the received keys.
+#include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
+#include <fcntl.h>
 #include <nccl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
 #include "../../include/onesweep_b200.h"
 #include "osb_internal.h"
@@ -35,6 +41,35 @@ inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? OSB200_OK : OS
         cudaError_t e__ = (expr);                        \
         if (e__ != cudaSuccess) return cuda_status(e__); \
     } while (0)
+// EXPERIMENT, off unless OSB_SHARDED_RENDEZVOUS is set: a host rendezvous of the ranks (POSIX shared memory, busy-polled) at
+// the entry of every sharded sort.  Round 2 measured, on this round's 4- and 8-GPU boxes, steps of 29 / 77 ms instead of round
+// 1's 17 / 18 ms with every kernel at its expected duration (MSD histogram 0.73, exchange 4.6, local sort 11.05 ms) and NCCL's
+// tiny collectives at 18-30 us in isolation: the time is skew between the ranks at the three collectives of a step
+// (profiles/r02_sharded_host_wait.txt).  Not the cause: the NVML sampler, host enqueue time (50 + 120 us per call), the way
+// the host waits (blocking or busy poll), NCCL's algorithm (NVLS / Ring / LL).  Starting the steps together with this
+// rendezvous made it worse (46 ms at N = 4), so the skew does not come from the hosts entering the call at different times.
+// Unresolved at the end of the round; N = 2 is unaffected (15.8 ms per step).
+inline void host_rendezvous(std::atomic<unsigned long long>* arrivals, int world)
+{
+    if (!arrivals || world < 2) return;
+    const unsigned long long ticket = arrivals->fetch_add(1, std::memory_order_acq_rel);
+    const unsigned long long target = (ticket / static_cast<unsigned long long>(world) + 1) * static_cast<unsigned long long>(world);
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (arrivals->load(std::memory_order_acquire) < target) {
+        for (int i = 0; i < 32; ++i) __builtin_ia32_pause();
+        if ((++spins & 0xfffu) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(1)) return;
+    }
+}
+
+// busy poll (see osb200_sharded_sort_keys_u32): returns as soon as the event has completed
+inline cudaError_t spin_until(cudaEvent_t e)
+{
+    cudaError_t r;
+    while ((r = cudaEventQuery(e)) == cudaErrorNotReady)
+        for (int i = 0; i < 32; ++i) __builtin_ia32_pause();
+    return r;
+}
 #define OSB_NCCL(expr)                                   \
     do {                                                 \
         ncclResult_t r__ = (expr);                       \
@@ -63,6 +98,12 @@ struct osb200_sharded_sorter {
     bool force_fine = false;  // always use the 256-bucket plan (tests)
     int last_bins = 0;
     cudaEvent_t ev[4] = {};
+    cudaEvent_t tev[3] = {};  // (OSB_SHARDED_TRACE) after the MSD histogram kernel, before / after the exchange kernel
+    bool tev_valid = false;
+    cudaEvent_t sync_ev = nullptr;  // host wait for the all-gathered histograms (busy-polled)
+    // host rendezvous of the ranks (all on one node) in POSIX shared memory: keeps the ranks' steps in phase, see host_rendezvous
+    std::atomic<unsigned long long>* shm_arrivals = nullptr;
+    char shm_name[48] = {};
     float last_ms[4] = {0, 0, 0, 0};
 };
 
@@ -143,6 +184,10 @@ int osb200_sharded_destroy(osb200_sharded_handle h)
     cudaFreeHost(h->h_out_base);
     cudaFreeHost(h->h_coarse_hist);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->tev) if (e) cudaEventDestroy(e);
+    if (h->sync_ev) cudaEventDestroy(h->sync_ev);
+    if (h->shm_arrivals) munmap(static_cast<void*>(h->shm_arrivals), 4096);
+    if (h->shm_name[0] && h->rank == 0) shm_unlink(h->shm_name);
     if (h->comm) ncclCommDestroy(h->comm);
     delete h;
     return OSB200_OK;
@@ -167,6 +212,21 @@ int osb200_sharded_create(osb200_sharded_handle* out, const void* unique_id_128_
     std::memcpy(&id, unique_id_128_bytes, sizeof(id));
     if (ncclCommInitRank(&s->comm, world, id, rank) != ncclSuccess) { osb200_sharded_destroy(s); return OSB200_ERR_NCCL; }
 
+    if (world > 1 && std::getenv("OSB_SHARDED_RENDEZVOUS")) {  // opt-in experiment (measured: it did not help, see host_rendezvous)
+        unsigned long long tag = 0;
+        std::memcpy(&tag, unique_id_128_bytes, sizeof(tag));
+        unsigned long long tag2 = 0;
+        std::memcpy(&tag2, static_cast<const char*>(unique_id_128_bytes) + 8, sizeof(tag2));
+        std::snprintf(s->shm_name, sizeof(s->shm_name), "/osb200_%016llx%016llx", tag, tag2);
+        const int fd = shm_open(s->shm_name, O_CREAT | O_RDWR, 0600);
+        if (fd >= 0) {
+            if (ftruncate(fd, 4096) == 0) {
+                void* p = mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+                if (p != MAP_FAILED) s->shm_arrivals = static_cast<std::atomic<unsigned long long>*>(p);  // zero-filled on creation
+            }
+            close(fd);
+        }
+    }
     int st = osb200_create(&s->exch, max_n_local, 4, 0);
     if (st == OSB200_OK) st = osb200_create(&s->local, s->capacity, 4, 0);
     if (st != OSB200_OK) { osb200_sharded_destroy(s); return st; }
@@ -179,6 +239,7 @@ int osb200_sharded_create(osb200_sharded_handle* out, const void* unique_id_128_
     ok = ok && cudaMallocHost(&s->h_out_base, kRadix * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMallocHost(&s->h_coarse_hist, kRadix * sizeof(unsigned long long)) == cudaSuccess;
     for (auto& e : s->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s->sync_ev, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { cudaGetLastError(); osb200_sharded_destroy(s); return OSB200_ERR_ALLOC; }
     cudaMemset(s->d_flag, 0, 64);
 
@@ -267,14 +328,42 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
     cudaStream_t q = static_cast<cudaStream_t>(stream);
     const int R = h->world;
 
+    // OSB_SHARDED_TRACE=1: host-side wall clock of this call's segments on stderr (diagnosis of straggling ranks)
+    static const bool trace = std::getenv("OSB_SHARDED_TRACE") != nullptr;
+    using clk = std::chrono::steady_clock;
+    if (h->shm_arrivals) host_rendezvous(h->shm_arrivals, R);
+    const clk::time_point t0 = clk::now();
+    if (trace) {
+        for (auto& e : h->tev) if (!e) OSB_TRY(cudaEventCreate(&e));
+        if (h->tev_valid) {  // kernel-only durations of the PREVIOUS call (its events have long completed)
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventSynchronize(h->ev[3]);
+            cudaEventElapsedTime(&a, h->ev[0], h->tev[0]);
+            cudaEventElapsedTime(&b, h->tev[0], h->ev[1]);
+            cudaEventElapsedTime(&c, h->ev[1], h->tev[1]);
+            cudaEventElapsedTime(&d, h->tev[1], h->tev[2]);
+            float e2 = 0;
+            cudaEventElapsedTime(&e2, h->tev[2], h->ev[2]);
+            std::fprintf(stderr, "[osb sharded rank %d] prev call: MSD hist kernel %.3f ms, allgather+D2H+sync+plan %.3f ms, barrier1+H2D %.3f ms, exchange kernel %.3f ms, barrier2 %.3f ms\n",
+                         h->rank, a, b, c, d, e2);
+        }
+    }
     OSB_TRY(cudaEventRecord(h->ev[0], q));
     // 1-2. most-significant-digit histogram, all-gather
     int st = osb_internal_digit_histogram(h->exch, d_keys_local, n_local, 24, h->d_hist, q);
     if (st != OSB200_OK) return st;
+    if (trace) OSB_TRY(cudaEventRecord(h->tev[0], q));
     OSB_NCCL(ncclAllGather(h->d_hist, h->d_hist_all, kRadix, ncclUint64, h->comm, q));
     OSB_TRY(cudaMemcpyAsync(h->h_hist_all, h->d_hist_all, static_cast<size_t>(R) * kRadix * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, q));
-    OSB_TRY(cudaStreamSynchronize(q));  // the plan (and the receive size) is needed on the host
+    const clk::time_point t1 = clk::now();
+    // The plan (and the receive size) is needed on the host.  The wait is a busy poll of an event, not
+    // cudaStreamSynchronize: the runtime's blocking wait backs off to a sleeping poll after a while, and a rank that wakes
+    // up late arrives late at the next collective -- measured at N = 4/8 as 9-13 ms of skew per barrier, steps of 30/77 ms
+    // instead of 17/18 (profiles/r02_sharded_host_wait.txt).
+    OSB_TRY(cudaEventRecord(h->sync_ev, q));
+    OSB_TRY(spin_until(h->sync_ev));
+    const clk::time_point t2 = clk::now();
 
     // 3. plan.  Preferred: R = 2^k ranks and the equal-width split of the key space fits the receive buffers ->
     //    exchange on the top k bits only (R bins instead of 256): runs of ~n/(tiles*R) keys (8 KB at R = 8) keep the
@@ -336,8 +425,10 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
             h->h_out_base[d] = peer / sizeof(uint32_t) + recv_off[d];  // virtual element index relative to address 0
         }
         OSB_TRY(cudaMemcpyAsync(h->d_out_base, h->h_out_base, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+        if (trace) OSB_TRY(cudaEventRecord(h->tev[1], q));
         st = osb_internal_binning_pass(h->exch, d_keys_local, nullptr, n_local, xshift, h->d_hist, h->d_out_base, q);
         if (st != OSB200_OK) return st;
+        if (trace) { OSB_TRY(cudaEventRecord(h->tev[2], q)); h->tev_valid = true; }
         // every rank's scatter kernel has completed (and its NVLink stores are performed) before any local sort starts
         OSB_NCCL(ncclAllReduce(h->d_flag, h->d_flag, 1, ncclUint32, ncclSum, h->comm, q));
     } else {
@@ -371,6 +462,12 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
     st = osb200_sort_keys_u32(h->local, h->recv_buf, mine, q);
     if (st != OSB200_OK) return st;
     OSB_TRY(cudaEventRecord(h->ev[3], q));
+    if (trace) {
+        const clk::time_point t3 = clk::now();
+        auto us = [](clk::time_point a, clk::time_point b) { return static_cast<long>(std::chrono::duration_cast<std::chrono::microseconds>(b - a).count()); };
+        std::fprintf(stderr, "[osb sharded rank %d] enqueue hist+allgather %ld us, wait %ld us, plan+enqueue exchange+local sort %ld us\n",
+                     h->rank, us(t0, t1), us(t1, t2), us(t2, t3));
+    }
     *d_out = h->recv_buf;
     *n_out = mine;
     return OSB200_OK;
@@ -379,7 +476,7 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
 int osb200_sharded_last_timing(osb200_sharded_handle h, float* out_ms4)
 {
     if (!h || !out_ms4) return OSB200_ERR_INVALID_ARG;
-    OSB_TRY(cudaEventSynchronize(h->ev[3]));
+    OSB_TRY(spin_until(h->ev[3]));
     OSB_TRY(cudaEventElapsedTime(&out_ms4[0], h->ev[0], h->ev[1]));
     OSB_TRY(cudaEventElapsedTime(&out_ms4[1], h->ev[1], h->ev[2]));
     OSB_TRY(cudaEventElapsedTime(&out_ms4[2], h->ev[2], h->ev[3]));
