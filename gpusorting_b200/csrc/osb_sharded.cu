@@ -78,6 +78,30 @@ inline cudaError_t spin_until(cudaEvent_t e)
 
 }  // namespace
 
+
+// ---- no copy-engine operations inside a step ------------------------------------------------------------------------------
+// The all-gathered histograms reach the host, and the plan reaches the device, through MAPPED pinned memory written / read by
+// tiny kernels on the same stream; the host polls a flag word in that memory.  Round 2 measured why (N = 4, kernel-only
+// events, profiles/r02_sharded_host_wait.txt): a rank that had waited 13 ms inside the all-gather kernel for a late peer saw
+// its device-to-host copy of the 8 KB result complete 9 ms after the ranks that had not waited -- a copy-engine operation
+// ordered behind a compute kernel that waited long starts late -- arrived late at the next barrier, made the others wait
+// there, and the skew sustained itself: 30 / 77 ms per step at N = 4 / 8 instead of 17 / 18.  Kernels follow kernels
+// without that penalty (the second barrier, ordered behind the exchange kernel, never showed it).
+__global__ void __launch_bounds__(256)
+publish_to_host_kernel(const unsigned long long* __restrict__ src, volatile unsigned long long* dst_mapped, int count,
+                       volatile unsigned long long* flag_mapped, unsigned long long step)
+{
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst_mapped[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) { *flag_mapped = step; __threadfence_system(); }
+}
+__global__ void __launch_bounds__(256)
+stage_from_host_kernel(const volatile unsigned long long* src_mapped, unsigned long long* __restrict__ dst, int count)
+{
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src_mapped[i];
+}
+
 struct osb200_sharded_sorter {
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
@@ -92,6 +116,14 @@ struct osb200_sharded_sorter {
     unsigned long long* h_hist_all = nullptr;  // pinned
     unsigned long long* h_out_base = nullptr;  // pinned
     unsigned long long* h_coarse_hist = nullptr;  // pinned
+    // device aliases of the three mapped pinned buffers above and of the flag word the host polls
+    unsigned long long* dm_hist_all = nullptr;
+    unsigned long long* dm_out_base = nullptr;
+    unsigned long long* dm_coarse_hist = nullptr;
+    unsigned long long* h_flag = nullptr;
+    unsigned long long* dm_flag = nullptr;
+    unsigned long long step = 0;
+    bool copy_engine = false;  // OSB_SHARDED_COPY_ENGINE=1: round 1's cudaMemcpyAsync path (diagnosis)
     uint32_t* d_flag = nullptr;                // 1-element all-reduce used as a stream-ordered cross-GPU barrier
     void* peer_recv[kMaxWorld] = {};           // IPC-mapped receive buffers of all ranks (own = recv_buf)
     bool fused = true;
@@ -183,6 +215,7 @@ int osb200_sharded_destroy(osb200_sharded_handle h)
     cudaFreeHost(h->h_hist_all);
     cudaFreeHost(h->h_out_base);
     cudaFreeHost(h->h_coarse_hist);
+    cudaFreeHost(h->h_flag);
     for (cudaEvent_t e : h->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->tev) if (e) cudaEventDestroy(e);
     if (h->sync_ev) cudaEventDestroy(h->sync_ev);
@@ -235,9 +268,21 @@ int osb200_sharded_create(osb200_sharded_handle* out, const void* unique_id_128_
     ok = ok && cudaMalloc(&s->d_hist_all, static_cast<size_t>(world) * kRadix * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&s->d_out_base, kRadix * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&s->d_flag, 64) == cudaSuccess;
-    ok = ok && cudaMallocHost(&s->h_hist_all, static_cast<size_t>(world) * kRadix * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&s->h_out_base, kRadix * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&s->h_coarse_hist, kRadix * sizeof(unsigned long long)) == cudaSuccess;
+    auto mapped = [&](unsigned long long** host, unsigned long long** dev, size_t count) {
+        void* hp = nullptr;
+        void* dp = nullptr;
+        if (cudaHostAlloc(&hp, count * sizeof(unsigned long long), cudaHostAllocMapped) != cudaSuccess) return false;
+        std::memset(hp, 0, count * sizeof(unsigned long long));
+        *host = static_cast<unsigned long long*>(hp);
+        if (cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) return false;
+        *dev = static_cast<unsigned long long*>(dp);
+        return true;
+    };
+    ok = ok && mapped(&s->h_hist_all, &s->dm_hist_all, static_cast<size_t>(world) * kRadix);
+    ok = ok && mapped(&s->h_out_base, &s->dm_out_base, kRadix);
+    ok = ok && mapped(&s->h_coarse_hist, &s->dm_coarse_hist, kRadix);
+    ok = ok && mapped(&s->h_flag, &s->dm_flag, 8);
+    s->copy_engine = std::getenv("OSB_SHARDED_COPY_ENGINE") != nullptr;
     for (auto& e : s->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s->sync_ev, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { cudaGetLastError(); osb200_sharded_destroy(s); return OSB200_ERR_ALLOC; }
@@ -354,15 +399,35 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
     if (st != OSB200_OK) return st;
     if (trace) OSB_TRY(cudaEventRecord(h->tev[0], q));
     OSB_NCCL(ncclAllGather(h->d_hist, h->d_hist_all, kRadix, ncclUint64, h->comm, q));
-    OSB_TRY(cudaMemcpyAsync(h->h_hist_all, h->d_hist_all, static_cast<size_t>(R) * kRadix * sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, q));
+    const unsigned long long step = ++h->step;
+    if (h->copy_engine)
+        OSB_TRY(cudaMemcpyAsync(h->h_hist_all, h->d_hist_all, static_cast<size_t>(R) * kRadix * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, q));
+    else
+    {
+        publish_to_host_kernel<<<1, 256, 0, q>>>(h->d_hist_all, h->dm_hist_all, R * kRadix, h->dm_flag, step);
+        OSB_TRY(cudaGetLastError());
+    }
     const clk::time_point t1 = clk::now();
-    // The plan (and the receive size) is needed on the host.  The wait is a busy poll of an event, not
-    // cudaStreamSynchronize: the runtime's blocking wait backs off to a sleeping poll after a while, and a rank that wakes
-    // up late arrives late at the next collective -- measured at N = 4/8 as 9-13 ms of skew per barrier, steps of 30/77 ms
-    // instead of 17/18 (profiles/r02_sharded_host_wait.txt).
+    // The plan (and the receive size) is needed on the host: the one host wait of a step.  It polls the flag word the
+    // publishing kernel writes into mapped pinned memory (see publish_to_host_kernel for why no copy engine is involved).
     OSB_TRY(cudaEventRecord(h->sync_ev, q));
-    OSB_TRY(spin_until(h->sync_ev));
+    if (h->copy_engine) {
+        OSB_TRY(spin_until(h->sync_ev));
+    } else {
+        // the flag is written by the kernel after a system-scope fence; the event (recorded behind the kernel) is the safety net
+        const volatile unsigned long long* flag = h->h_flag;
+        unsigned polls = 0;
+        while (*flag != step) {
+            for (int i = 0; i < 16; ++i) __builtin_ia32_pause();
+            if ((++polls & 0x3ffu) == 0) {
+                const cudaError_t r = cudaEventQuery(h->sync_ev);
+                if (r == cudaSuccess) break;  // the kernel has completed: its writes are visible
+                if (r != cudaErrorNotReady) return cuda_status(r);
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
     const clk::time_point t2 = clk::now();
 
     // 3. plan.  Preferred: R = 2^k ranks and the equal-width split of the key space fits the receive buffers ->
@@ -400,7 +465,13 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
         for (int d = 0; d < kRadix; ++d) h->h_out_base[d / per] += my_hist[d];
         // (staged through its own pinned buffer: no host sync needed before h_out_base is filled again below)
         std::memcpy(h->h_coarse_hist, h->h_out_base, kRadix * sizeof(unsigned long long));
-        OSB_TRY(cudaMemcpyAsync(h->d_hist, h->h_coarse_hist, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+        if (h->copy_engine)
+            OSB_TRY(cudaMemcpyAsync(h->d_hist, h->h_coarse_hist, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+        else
+        {
+            stage_from_host_kernel<<<1, 256, 0, q>>>(h->dm_coarse_hist, h->d_hist, kRadix);
+            OSB_TRY(cudaGetLastError());
+        }
     } else {
         st = osb200_sharded_plan(reinterpret_cast<const uint64_t*>(h->h_hist_all), R, h->rank, dest, recv_count, recv_off);
         if (st != OSB200_OK) return st;
@@ -424,7 +495,13 @@ int osb200_sharded_sort_keys_u32(osb200_sharded_handle h, const uint32_t* d_keys
             const unsigned long long peer = reinterpret_cast<unsigned long long>(h->peer_recv[dest[d]]);
             h->h_out_base[d] = peer / sizeof(uint32_t) + recv_off[d];  // virtual element index relative to address 0
         }
-        OSB_TRY(cudaMemcpyAsync(h->d_out_base, h->h_out_base, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+        if (h->copy_engine)
+            OSB_TRY(cudaMemcpyAsync(h->d_out_base, h->h_out_base, kRadix * sizeof(unsigned long long), cudaMemcpyHostToDevice, q));
+        else
+        {
+            stage_from_host_kernel<<<1, 256, 0, q>>>(h->dm_out_base, h->d_out_base, kRadix);
+            OSB_TRY(cudaGetLastError());
+        }
         if (trace) OSB_TRY(cudaEventRecord(h->tev[1], q));
         st = osb_internal_binning_pass(h->exch, d_keys_local, nullptr, n_local, xshift, h->d_hist, h->d_out_base, q);
         if (st != OSB200_OK) return st;

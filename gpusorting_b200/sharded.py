@@ -213,13 +213,17 @@ def bench_sharded(args, rank: int, world: int, local_rank: int, n: int):
     sampler = ClockSampler(local_rank)
     sampler.start()
     torch.cuda.synchronize()
+    # The host does not wait for the GPU between the steps (each step still has its one host wait inside the call, for the
+    # plan): it enqueues step i+1's histogram while step i's local sort runs, as a pipelining caller would.  Waiting here after
+    # every step put every host stall (10-20 ms ones were seen with >= 4 ranks on a box) on the critical path of ALL ranks
+    # through the next collective.  The phase times reported are those of the last timed step.
     events, phases, local_prof = [], [], []
     for _ in range(args.steps):
         a, b, res = one_step()
         events.append((a, b))
-        phases.append(s.last_timing())
-        local_prof.append(s.local_profile())
     torch.cuda.synchronize()
+    phases.append(s.last_timing())
+    local_prof.append(s.local_profile())
     dist.barrier()
     clocks = sampler.result()
     ms = sum(a.elapsed_time(b) for a, b in events) / args.steps
