@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../gpusorting_b200/csrc"
 mkdir -p ../../tools/sweep
 rm -f ../../tools/sweep/*.so
-CONFIGS=${CONFIGS:-"16 32 2 8 4 0;16 32 2 8 4 1;16 32 2 8 4 2;16 32 2 8 4 3"}
+CONFIGS=${CONFIGS:-"16 32 2 16 8 0;16 32 2 32 8 0;16 32 2 16 8 4"}
 IFS=';' read -ra CFGS <<< "$CONFIGS"
 for cfg in "${CFGS[@]}"; do
   set -- $cfg
