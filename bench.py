@@ -48,10 +48,18 @@ def _physical_cores() -> int:
 
 HOST_THREADS = _physical_cores()
 # The CPU legs use every physical core, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1).  Must happen
-# before numpy / torch / the oracle load an OpenMP runtime.
-os.environ["OMP_NUM_THREADS"] = str(HOST_THREADS)
-os.environ.setdefault("OMP_PROC_BIND", "spread")
-os.environ.setdefault("OMP_PLACES", "cores")
+# before numpy / torch / the oracle load an OpenMP runtime.  ONLY for processes that run a CPU leg (the single-GPU arm's
+# cpu_baseline, the --impl reference arm): OMP_PROC_BIND pins the MAIN thread of the process to the first place as soon as
+# the OpenMP runtime loads, i.e. with N ranks on a box all N main threads land on core 0 and time-share it.  Round 2 found
+# that the hard way: with the binding set in every rank the sharded step took 30 / 77 ms at N = 4 / 8 instead of 17 / 18
+# (profiles/r02_sharded_host_wait.txt) -- the rank whose busy-polling thread had run longest was descheduled and reacted
+# to its GPU ~10 ms late, at every collective.
+_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+_CPU_ARM = "reference" in sys.argv[1:]
+if _WORLD == 1 or _CPU_ARM:
+    os.environ["OMP_NUM_THREADS"] = str(HOST_THREADS)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
 
 LOG2_N = 30            # BASELINE.json configs[1]: 2^30 uint32 keys-only, uniform random, 1xB200
 METRIC = "OneSweep sort throughput, 2^30 uint32 keys per GPU, keys-only, uniform-random"  # both arms print this string

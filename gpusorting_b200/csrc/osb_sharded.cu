@@ -79,14 +79,12 @@ inline cudaError_t spin_until(cudaEvent_t e)
 }  // namespace
 
 
-// ---- no copy-engine operations inside a step ------------------------------------------------------------------------------
+// ---- EXPERIMENT (OSB_SHARDED_MAPPED=1, never measured): no copy-engine operations inside a step ---------------------------
 // The all-gathered histograms reach the host, and the plan reaches the device, through MAPPED pinned memory written / read by
-// tiny kernels on the same stream; the host polls a flag word in that memory.  Round 2 measured why (N = 4, kernel-only
-// events, profiles/r02_sharded_host_wait.txt): a rank that had waited 13 ms inside the all-gather kernel for a late peer saw
-// its device-to-host copy of the 8 KB result complete 9 ms after the ranks that had not waited -- a copy-engine operation
-// ordered behind a compute kernel that waited long starts late -- arrived late at the next barrier, made the others wait
-// there, and the skew sustained itself: 30 / 77 ms per step at N = 4 / 8 instead of 17 / 18.  Kernels follow kernels
-// without that penalty (the second barrier, ordered behind the exchange kernel, never showed it).
+// tiny kernels on the same stream; the host polls a flag word in that memory.  Written while chasing the N = 4 / 8 skew of
+// round 2 (profiles/r02_sharded_host_wait.txt) under the hypothesis that a copy ordered behind a long-waiting compute kernel
+// starts late; the skew turned out to come from the benchmark pinning every rank's main thread to core 0 (OMP_PROC_BIND, see
+// bench.py), and the round's GPU budget was spent before this path could run once.  Kept for the next round to measure.
 __global__ void __launch_bounds__(256)
 publish_to_host_kernel(const unsigned long long* __restrict__ src, volatile unsigned long long* dst_mapped, int count,
                        volatile unsigned long long* flag_mapped, unsigned long long step)
@@ -123,7 +121,7 @@ struct osb200_sharded_sorter {
     unsigned long long* h_flag = nullptr;
     unsigned long long* dm_flag = nullptr;
     unsigned long long step = 0;
-    bool copy_engine = false;  // OSB_SHARDED_COPY_ENGINE=1: round 1's cudaMemcpyAsync path (diagnosis)
+    bool copy_engine = true;   // cudaMemcpyAsync for the 8 KB readback and the 4 KB plan; OSB_SHARDED_MAPPED=1: the kernels below
     uint32_t* d_flag = nullptr;                // 1-element all-reduce used as a stream-ordered cross-GPU barrier
     void* peer_recv[kMaxWorld] = {};           // IPC-mapped receive buffers of all ranks (own = recv_buf)
     bool fused = true;
@@ -282,7 +280,7 @@ int osb200_sharded_create(osb200_sharded_handle* out, const void* unique_id_128_
     ok = ok && mapped(&s->h_out_base, &s->dm_out_base, kRadix);
     ok = ok && mapped(&s->h_coarse_hist, &s->dm_coarse_hist, kRadix);
     ok = ok && mapped(&s->h_flag, &s->dm_flag, 8);
-    s->copy_engine = std::getenv("OSB_SHARDED_COPY_ENGINE") != nullptr;
+    s->copy_engine = std::getenv("OSB_SHARDED_MAPPED") == nullptr;  // default: cudaMemcpyAsync (the measured path)
     for (auto& e : s->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s->sync_ev, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { cudaGetLastError(); osb200_sharded_destroy(s); return OSB200_ERR_ALLOC; }

@@ -53,3 +53,23 @@ def test_both_arms_print_the_same_metric_and_workload_strings():
     assert d["metric"] == bench.METRIC and d["config"]["workload"] == bench.workload(bench.LOG2_N, 2)
     # torchrun exports OMP_NUM_THREADS=1: the CPU leg must still use every physical core it may run on
     assert d["cpu_baseline"]["cores"] == bench.HOST_THREADS >= 1
+
+
+def test_gpu_arm_under_torchrun_does_not_pin_its_main_thread():
+    """Round 2's N = 4 / 8 scaling regression: bench.py exported OMP_PROC_BIND in every rank, the OpenMP runtime then pinned
+    every rank's main thread to core 0, and the ranks time-shared one core.  A rank of the GPU arm (WORLD_SIZE > 1, no
+    --impl reference) must keep the launcher's OMP settings and its affinity mask; the CPU arm keeps the binding."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os,sys; sys.argv=['bench.py'{extra}]; os.environ['WORLD_SIZE']='4'; os.environ['RANK']='1'; "
+            "os.environ['OMP_NUM_THREADS']='1'; os.environ.pop('OMP_PROC_BIND', None); os.environ.pop('OMP_PLACES', None); before=len(os.sched_getaffinity(0)); "
+            "import importlib.util as u; s=u.spec_from_file_location('bench', os.path.join(r'" + root + "', 'bench.py')); "
+            "m=u.module_from_spec(s); s.loader.exec_module(m); import torch; "
+            "print(before, len(os.sched_getaffinity(0)), os.environ.get('OMP_PROC_BIND'), os.environ['OMP_NUM_THREADS'])")
+    out = subprocess.run([sys.executable, "-c", code.format(extra=",'--gpus','4'")], capture_output=True, text=True, timeout=300)
+    before, after, bind, threads = out.stdout.split()
+    assert before == after and bind == "None" and threads == "1", out.stdout + out.stderr
+    out = subprocess.run([sys.executable, "-c", code.format(extra=",'--impl','reference'")], capture_output=True, text=True, timeout=300)
+    assert out.stdout.split()[2] == "spread", out.stdout + out.stderr
