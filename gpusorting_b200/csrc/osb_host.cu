@@ -7,7 +7,9 @@
 //   * no per-sort memset of the 64-bit inclusive descriptors (epoch-stamped); per sort there are two memsets: the 8.3 KB
 //     control block (global histogram + tile tickets) and the compact 16-bit reductions (512 B per tile and place:
 //     128 MiB at n = 2^30 u32, ~20 us) -- against the reference's 6 memsets over ~573 MB at n = 2^30;
-//   * passes whose digit is the same for every key are skipped, decided on the device (osb::SortPlan);
+//   * passes whose digit is the same for every key are skipped, and passes with one dominant bin run in the HOT
+//     instantiation of the pass, both decided on the device (osb::SortPlan);
+//   * a sort of at most one tile is ONE launch of the single-CTA shared-memory sort (also the segmented sort);
 //   * no host synchronisation inside the sort; everything is enqueued on the caller's stream;
 //   * the caller owns keys/values.
 #include <cstdio>
@@ -21,7 +23,7 @@
 
 namespace {
 
-constexpr int kVersion = 1001;
+constexpr int kVersion = 1002;  // round 2: device plan, bit ranges, forward-progress fallback, hot passes, segmented sort
 constexpr int kMaxPlaces = 8;
 
 inline int cuda_status(cudaError_t e) { return e == cudaSuccess ? OSB200_OK : OSB200_ERR_CUDA - static_cast<int>(e); }
